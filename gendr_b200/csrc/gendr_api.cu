@@ -1,0 +1,370 @@
+// gendr_api.cu -- host side of libgendr_b200.so: the C ABI declared in include/gendr_b200.h.
+// Derives the launch constants, owns the workspace layout, dispatches to the per-distribution kernel launchers
+// (inst_dist.cu) and reports errors.  No torch, no CPU compute path: every entry point runs CUDA kernels.
+#include "../../include/gendr_b200.h"
+#include "render_kernels.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+
+namespace gendr {
+#define GENDR_DECL(k) cudaError_t launch_render_dist_##k(const RenderParams&, const KernelIO&, const LaunchCfg&);
+GENDR_DECL(0) GENDR_DECL(1) GENDR_DECL(2) GENDR_DECL(3) GENDR_DECL(4) GENDR_DECL(5) GENDR_DECL(6) GENDR_DECL(7) GENDR_DECL(8)
+GENDR_DECL(9) GENDR_DECL(10) GENDR_DECL(11) GENDR_DECL(12) GENDR_DECL(13) GENDR_DECL(14) GENDR_DECL(15) GENDR_DECL(16) GENDR_DECL(17)
+#undef GENDR_DECL
+static const render_launch_fn kLaunchTable[D_COUNT] = {
+    launch_render_dist_0,  launch_render_dist_1,  launch_render_dist_2,  launch_render_dist_3,  launch_render_dist_4,
+    launch_render_dist_5,  launch_render_dist_6,  launch_render_dist_7,  launch_render_dist_8,  launch_render_dist_9,
+    launch_render_dist_10, launch_render_dist_11, launch_render_dist_12, launch_render_dist_13, launch_render_dist_14,
+    launch_render_dist_15, launch_render_dist_16, launch_render_dist_17};
+
+// ---- preprocessing kernel: one thread per (batch, face) -------------------------------------------------------
+__global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ RenderParams P, const float* __restrict__ faces,
+                                                   float* __restrict__ records, uint2* __restrict__ rects,
+                                                   float* __restrict__ faces_info) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)P.B * P.F) return;
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = __ldg(faces + i * 9 + k);
+    float rec[REC_WORDS];
+    prep_face_record(v, rec, faces_info ? faces_info + i * 27 : nullptr, P);
+    float4* dst = reinterpret_cast<float4*>(records + i * REC_WORDS);
+#pragma unroll
+    for (int k = 0; k < REC_WORDS / 4; ++k) dst[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+    rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+}
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* what) {
+    if (code >= GENDR_ERR_INVALID_ARGUMENT) snprintf(g_err, sizeof g_err, "gendr_b200: %s", what);
+    else snprintf(g_err, sizeof g_err, "gendr_b200: %s: %s", what, cudaGetErrorString((cudaError_t)code));
+    return code;
+}
+#define GENDR_CUDA(call, what)                                      \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return fail((int)e__, what);        \
+    } while (0)
+
+// NDC radius beyond which an OUTSIDE pixel (sign = -1) is guaranteed to fall under the 1e-6 probability threshold
+// of K.cu:784 (in units of x; squared distances handled by the caller).  INF = never.  Constants are the analytic
+// crossing points, nudged up where the fp32 evaluation is quantised near the threshold.
+static double cull_x_over_tau(int dist, double shift) {
+    const double INF = std::numeric_limits<double>::infinity();
+    switch (dist) {
+    case D_HARD: return 0.0;
+    case D_UNIFORM: case D_CUBIC_HERMITE: case D_WIGNER: return 1.0;
+    case D_GAUSSIAN: return 4.7535;
+    case D_LAPLACE: return 13.1225;
+    case D_LOGISTIC: return 13.8156;
+    case D_GUDERMANNIAN: return 13.37;
+    case D_CAUCHY: return 3.5e5;
+    case D_RECIPROCAL: return 5.5e5;
+    case D_GUMBEL_MAX: return 2.6259;
+    case D_GUMBEL_MIN: return 13.9;
+    case D_EXPONENTIAL: case D_GAMMA: case D_LEVY: return shift > 0 ? shift : 0.0;
+    case D_EXPONENTIAL_REV: return (13.9 - shift) > 0 ? (13.9 - shift) : 0.0;
+    case D_GAMMA_REV: return (15.01 - shift) > 0 ? (15.01 - shift) : 0.0;
+    case D_LEVY_REV: return INF;
+    }
+    return INF;
+}
+
+static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_params* u) {
+    if (!u) return GENDR_ERR_INVALID_ARGUMENT;
+    if (B < 0 || F < 0 || T < 1 || u->image_size < 1 || u->image_size > 32767) return GENDR_ERR_INVALID_ARGUMENT;
+    if (u->dist_func < 0 || u->dist_func >= D_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
+    if (u->aggr_alpha_func < 0 || u->aggr_alpha_func >= T_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
+    memset(&P, 0, sizeof P);
+    P.B = B; P.F = F; P.S = u->image_size; P.T = T;
+    P.R = (int)sqrt((double)T);                          // K.cu:1098
+    P.dist_func = u->dist_func; P.aggr_alpha_func = u->aggr_alpha_func; P.aggr_rgb_func = u->aggr_rgb_func;
+    P.texture_type = u->texture_type; P.dist_squared = u->dist_squared ? 1 : 0; P.double_side = u->double_side ? 1 : 0;
+    P.dist_scale = u->dist_scale; P.dist_shape = u->dist_shape; P.dist_shift = u->dist_shift; P.dist_eps = u->dist_eps;
+    P.tcn_p = u->aggr_alpha_t_conorm_p; P.rgb_eps = u->aggr_rgb_eps; P.rgb_gamma = u->aggr_rgb_gamma;
+    P.near_ = u->near_plane; P.far_ = u->far_plane;
+    P.bg[0] = u->background[0]; P.bg[1] = u->background[1]; P.bg[2] = u->background[2];
+    P.thr = u->dist_eps * u->dist_scale;                 // fp32 product, K.cu:725
+    P.sqrt_thr = sqrtf(P.thr);                           // K.cu:747 (IEEE sqrt on both sides)
+    double c = cull_x_over_tau(u->dist_func, (double)u->dist_shift);
+    double r = c * (double)u->dist_scale;
+    if (u->dist_squared) r = std::sqrt(r);
+    if (!(u->dist_scale > 0.f) || !(r == r)) r = std::numeric_limits<double>::infinity();
+    P.cull_radius = (float)r;
+    P.gamma_kummer0 = (float)(1. / std::tgamma((double)u->dist_shape + 1.));
+    P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
+    P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
+    P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
+    P.super_chunk = F < 8192 ? ((F + 255) / 256) * 256 : 8192;
+    if (P.super_chunk < 256) P.super_chunk = 256;
+    return 0;
+}
+
+static size_t smem_bytes(const RenderParams& P) {
+    const int n_sc = P.super_chunk;
+    const int Fw = ((n_sc + NWARPS - 1) / NWARPS + 31) & ~31;
+    return (size_t)2 * STAGE_FACES * REC_WORDS * 4 + 2 * STAGE_FACES * 4 + 2 * 8 + 12 * 4 + (size_t)NWARPS * Fw * 2;
+}
+
+struct DeviceScope {   // run on the device that owns the data, restore the caller's device afterwards
+    int prev = -1, cur = -1;
+    cudaError_t enter(const void* p) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        cur = prev;
+        cudaPointerAttributes a;
+        if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) cur = a.device;
+        else (void)cudaGetLastError();
+        if (cur != prev) return cudaSetDevice(cur);
+        return cudaSuccess;
+    }
+    ~DeviceScope() { if (prev >= 0 && cur != prev) cudaSetDevice(prev); }
+};
+
+static float* ws_records(void* ws) { return reinterpret_cast<float*>(ws); }
+static uint2* ws_rects(void* ws, int B, int F) {
+    size_t rec_bytes = ((size_t)B * F * REC_BYTES + 255) & ~(size_t)255;
+    return reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + rec_bytes);
+}
+
+static int run_prep(const RenderParams& P, const float* faces, float* faces_info, void* ws, cudaStream_t st) {
+    const long long n = (long long)P.B * P.F;
+    if (n == 0) return 0;
+    prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, faces, ws_records(ws), ws_rects(ws, P.B, P.F), faces_info);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "prep_kernel launch");
+    return 0;
+}
+
+static int run_render(const RenderParams& P, const KernelIO& io, bool backward, cudaStream_t st) {
+    if (P.B == 0) return 0;
+    LaunchCfg cfg;
+    cfg.grid = dim3((unsigned)(P.B * P.tiles_x * P.tiles_y));
+    cfg.smem = smem_bytes(P);
+    cfg.stream = st;
+    cfg.backward = backward;
+    cfg.parametric = P.aggr_alpha_func >= T_HAMACHER;
+    cudaError_t e = kLaunchTable[P.dist_func](P, io, cfg);
+    g_launches++;
+    if (e != cudaSuccess) return fail((int)e, backward ? "backward render_kernel launch" : "forward render_kernel launch");
+    return 0;
+}
+
+// ---- scalar functions: one device thread, same templates as the render kernels --------------------------------
+template <int D> struct DistEval {
+    static __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P) {
+        if (id == D) return pdf ? dist_pdf<D>(s, x, P) : dist_cdf<D>(s, x, P);
+        return DistEval<D + 1>::run(id, pdf, s, x, P);
+    }
+};
+template <> struct DistEval<D_COUNT> {
+    static __device__ float run(int, bool, float, float, const RenderParams&) { return CUDART_NAN_F; }
+};
+__global__ void scalar_kernel(const __grid_constant__ RenderParams P, int what, int id, float a, float b, float* out) {
+    float r;
+    if (what == 0) r = DistEval<0>::run(id, false, a, b, P);
+    else if (what == 1) r = DistEval<0>::run(id, true, a, b, P);
+    else if (what == 2) r = (id >= T_HAMACHER) ? tconorm_fold<true>(id, a, b, P) : tconorm_fold<false>(id, a, b, P);
+    else r = (id >= T_HAMACHER) ? tconorm_dS<true>(id, a, b, P) : tconorm_dS<false>(id, a, b, P);
+    *out = r;
+}
+
+static float run_scalar(int what, int id, float a, float b, float scale, float shape, float shift, float p) {
+    gendr_render_params u;
+    memset(&u, 0, sizeof u);
+    u.image_size = 1; u.dist_func = (what < 2 && id >= 0 && id < D_COUNT) ? id : 0; u.dist_scale = scale; u.dist_shape = shape;
+    u.dist_shift = shift; u.dist_eps = 1.f; u.aggr_alpha_func = (what >= 2 && id >= 0 && id < T_COUNT) ? id : 0;
+    u.aggr_alpha_t_conorm_p = p; u.aggr_rgb_gamma = 1.f;
+    RenderParams P;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    if (make_params(P, 1, 1, 1, &u) != 0) return nan;
+    if ((what < 2 && (id < 0 || id >= D_COUNT)) || (what >= 2 && (id < 1 || id >= T_COUNT))) return nan;
+    float* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) { fail((int)cudaGetLastError(), "scalar cudaMalloc"); return nan; }
+    scalar_kernel<<<1, 1>>>(P, what, id, a, b, d);
+    g_launches++;
+    float h = nan;
+    cudaError_t e = cudaMemcpy(&h, d, sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { fail((int)e, "scalar kernel"); return nan; }
+    return h;
+}
+
+// ---- geometry probe -----------------------------------------------------------------------------------------
+__global__ void probe_kernel(const __grid_constant__ RenderParams P, const float* faces, const float* xy, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[9], rec[REC_WORDS];
+    for (int k = 0; k < 9; ++k) v[k] = faces[(size_t)i * 9 + k];
+    prep_face_record(v, rec, nullptr, P);
+    PairGeom g;
+    const float xp = xy[2 * i], yp = xy[2 * i + 1];
+    pair_barycentric(g, rec, xp, yp);
+    pair_project(g, rec, xp, yp, __float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+    float* o = out + (size_t)i * 10;
+    o[0] = g.w0; o[1] = g.w1; o[2] = g.w2; o[3] = g.t0; o[4] = g.t1; o[5] = g.t2; o[6] = g.dx; o[7] = g.dy; o[8] = g.sign;
+    o[9] = sop2(g.dx, g.dx, g.dy, g.dy);
+}
+
+// ---- cached device scratch for the host-buffer entry point -----------------------------------------------------
+struct HostPathScratch {
+    std::mutex mu;
+    int device = -1;
+    size_t cap = 0;
+    char* base = nullptr;
+    cudaStream_t stream = nullptr;
+};
+static HostPathScratch g_scratch;
+
+}  // namespace gendr
+
+using namespace gendr;
+
+extern "C" {
+
+const char* gendr_last_error(void) { return g_err; }
+const char* gendr_version(void) { return "gendr_b200 0.1 (sm_100a)"; }
+long long gendr_launch_count(void) { return g_launches.load(); }
+
+size_t gendr_workspace_bytes(int batch, int faces) {
+    if (batch < 0 || faces < 0) return 0;
+    size_t rec = ((size_t)batch * faces * REC_BYTES + 255) & ~(size_t)255;
+    size_t rct = ((size_t)batch * faces * sizeof(uint2) + 255) & ~(size_t)255;
+    return rec + rct + 256;
+}
+
+int gendr_forward_render(const float* faces, const float* textures, float* faces_info, float* aggrs_info,
+                         float* soft_colors, int batch, int num_faces, int texture_size,
+                         const gendr_render_params* params, int background_prefilled,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_forward_render");
+    if (batch == 0) return 0;
+    if (!faces || !textures || !aggrs_info || !soft_colors || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (int e = run_prep(P, faces, faces_info, workspace, st)) return e;
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
+    io.soft_colors = soft_colors; io.aggrs = aggrs_info; io.bg_from_buffer = background_prefilled ? 1 : 0;
+    return run_render(P, io, false, st);
+}
+
+int gendr_backward_render(const float* faces, const float* textures, const float* soft_colors,
+                          const float* aggrs_info, float* grad_faces, float* grad_textures,
+                          const float* grad_soft_colors, int batch, int num_faces, int texture_size,
+                          const gendr_render_params* params, int workspace_valid, int zero_grads,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render");
+    if (batch == 0) return 0;
+    if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_soft_colors || !workspace)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!workspace_valid) if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
+    if (zero_grads) {
+        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
+        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
+    }
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
+    io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
+    io.grad_colors = grad_soft_colors; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
+    return run_render(P, io, true, st);
+}
+
+int gendr_render_forward_backward_host(const float* h_faces, const float* h_textures, const float* h_grad_soft_colors,
+                                       float* h_soft_colors, float* h_grad_faces, float* h_grad_textures,
+                                       int batch, int num_faces, int texture_size, const gendr_render_params* params) {
+    if (!params || !h_faces || !h_textures || !h_soft_colors) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_render_forward_backward_host");
+    const size_t S = (size_t)params->image_size;
+    const size_t n_faces = (size_t)batch * num_faces * 9 * 4, n_tex = (size_t)batch * num_faces * texture_size * 3 * 4;
+    const size_t n_col = (size_t)batch * 4 * S * S * 4, n_agg = (size_t)batch * 2 * S * S * 4;
+    const size_t n_ws = gendr_workspace_bytes(batch, num_faces);
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const bool bwd = h_grad_soft_colors && h_grad_faces;
+    const size_t need = al(n_faces) * 2 + al(n_tex) * 2 + al(n_col) * 2 + al(n_agg) + al(n_ws);
+    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    int dev = 0;
+    GENDR_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    if (g_scratch.device != dev || g_scratch.cap < need) {
+        if (g_scratch.base) { cudaSetDevice(g_scratch.device); cudaFree(g_scratch.base); cudaSetDevice(dev); g_scratch.base = nullptr; g_scratch.cap = 0; }
+        if (!g_scratch.stream || g_scratch.device != dev) GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        GENDR_CUDA(cudaMalloc(&g_scratch.base, need), "cudaMalloc of host-path scratch");
+        g_scratch.cap = need; g_scratch.device = dev;
+    }
+    cudaStream_t st = g_scratch.stream;
+    char* p = g_scratch.base;
+    float* d_faces = (float*)p; p += al(n_faces);
+    float* d_gfaces = (float*)p; p += al(n_faces);
+    float* d_tex = (float*)p; p += al(n_tex);
+    float* d_gtex = (float*)p; p += al(n_tex);
+    float* d_col = (float*)p; p += al(n_col);
+    float* d_gcol = (float*)p; p += al(n_col);
+    float* d_agg = (float*)p; p += al(n_agg);
+    void* d_ws = p;
+    GENDR_CUDA(cudaMemcpyAsync(d_faces, h_faces, n_faces, cudaMemcpyHostToDevice, st), "H2D faces");
+    GENDR_CUDA(cudaMemcpyAsync(d_tex, h_textures, n_tex, cudaMemcpyHostToDevice, st), "H2D textures");
+    if (bwd) GENDR_CUDA(cudaMemcpyAsync(d_gcol, h_grad_soft_colors, n_col, cudaMemcpyHostToDevice, st), "H2D grad_soft_colors");
+    if (int e = gendr_forward_render(d_faces, d_tex, nullptr, d_agg, d_col, batch, num_faces, texture_size, params, 0, d_ws, n_ws, st)) return e;
+    if (bwd) {
+        if (int e = gendr_backward_render(d_faces, d_tex, d_col, d_agg, d_gfaces, h_grad_textures ? d_gtex : nullptr, d_gcol, batch, num_faces,
+                                          texture_size, params, 1, 1, d_ws, n_ws, st)) return e;
+    }
+    GENDR_CUDA(cudaMemcpyAsync(h_soft_colors, d_col, n_col, cudaMemcpyDeviceToHost, st), "D2H soft_colors");
+    if (bwd) {
+        GENDR_CUDA(cudaMemcpyAsync(h_grad_faces, d_gfaces, n_faces, cudaMemcpyDeviceToHost, st), "D2H grad_faces");
+        if (h_grad_textures) GENDR_CUDA(cudaMemcpyAsync(h_grad_textures, d_gtex, n_tex, cudaMemcpyDeviceToHost, st), "D2H grad_textures");
+    }
+    GENDR_CUDA(cudaStreamSynchronize(st), "host-path stream synchronize");
+    return 0;
+}
+
+float gendr_sigmoid_forward(int id, float sign, float x, float scale, float shape, float shift) {
+    return run_scalar(0, id, sign, x, scale, shape, shift, 0.f);
+}
+float gendr_sigmoid_backward(int id, float sign, float x, float scale, float shape, float shift) {
+    return run_scalar(1, id, sign, x, scale, shape, shift, 0.f);
+}
+float gendr_t_conorm_forward(int id, float a_existing, float b_new, int face_id, float p) {
+    (void)face_id;
+    return run_scalar(2, id, a_existing, b_new, 1.f, 0.f, 0.f, p);
+}
+float gendr_t_conorm_backward(int id, float a_all, float b_current, int number_of_faces, float p) {
+    (void)number_of_faces;
+    return run_scalar(3, id, a_all, b_current, 1.f, 0.f, 0.f, p);
+}
+
+int gendr_probe_pairs(const float* faces, const float* xy, float* out, int n, void* stream) {
+    if (n <= 0) return 0;
+    gendr_render_params u;
+    memset(&u, 0, sizeof u);
+    u.image_size = 256; u.dist_func = D_UNIFORM; u.dist_scale = 1e-2f; u.dist_eps = 1e4f; u.aggr_alpha_func = T_PROBABILISTIC;
+    u.aggr_rgb_gamma = 1.f;
+    RenderParams P;
+    if (int e = make_params(P, 1, 1, 1, &u)) return fail(e, "probe params");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(faces), "selecting device");
+    probe_kernel<<<(n + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(P, faces, xy, out, n);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "probe_kernel launch");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+"""Autograd binding of the B200 soft rasterizer -- the replacement for the reference's `GenDRFunction`
+(/root/reference/gendr/functional/renderer.py:11-236) and `render()` (:239-288).
+
+Same call surface (names, defaults, name-or-id arguments, asserts), but the lean path: outputs come from
+torch.empty and are fully written by one forward launch (the reference does 2 clones, 3 fills and 3 in-place scales
+first, renderer.py:130-151), the per-face records computed in forward are kept for backward, and texture gradients
+are only produced when `textures.requires_grad`.
+"""
+import torch
+from torch.autograd import Function
+
+from ..cuda import generalized_renderer as _ext
+
+# name -> id maps of the reference (functional/renderer.py:44-83)
+DIST_FUNC_IDS = {
+    'hard': 0, 'heaviside': 0,
+    'uniform': 1, 'cubic_hermite': 2, 'wigner_semicircle': 3,
+    'gaussian': 4, 'laplace': 5, 'logistic': 6, 'gudermannian': 7, 'hyperbolic_secant': 7,
+    'cauchy': 8, 'reciprocal': 9,
+    'gumbel_max': 10, 'gumbel_min': 11, 'exponential': 12, 'exponential_rev': 13,
+    'gamma': 14, 'gamma_rev': 15, 'levy': 16, 'levy_rev': 17,
+}
+AGGR_ALPHA_FUNC_IDS = {
+    'hard': 0, 'max': 1, 'probabilistic': 2, 'einstein': 3, 'hamacher': 4, 'frank': 5, 'yager': 6,
+    'aczel_alsina': 7, 'dombi': 8, 'schweizer_sklar': 9,
+}
+AGGR_RGB_FUNC_IDS = {'hard': 0, 'softmax': 1}
+TEXTURE_TYPE_IDS = {'surface': 0, 'vertex': 1}
+
+
+def _resolve(value, table):
+    # ints pass through (experiments/opt_shape.py:150,156 call with ids); unknown names raise KeyError like the reference
+    return value if isinstance(value, int) else table[value]
+
+
+class GenDRFunction(Function):
+    @staticmethod
+    def forward(ctx, face_vertices, textures, image_size=256, background_color=[0, 0, 0],
+                dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None,
+                dist_eps=1e4, aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
+                aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3, near=1, far=100,
+                double_side=True, texture_type='surface'):
+        assert dist_scale >= 0, dist_scale      # functional/renderer.py:96
+        assert dist_eps >= 1, dist_eps          # functional/renderer.py:101
+        if not face_vertices.is_cuda:
+            raise TypeError('GenDR only supports CUDA Tensors.')
+        params = _ext.make_params(
+            image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
+            _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
+            _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
+            TEXTURE_TYPE_IDS[texture_type], background_color)
+
+        faces = face_vertices.detach().to(torch.float32).contiguous()
+        B, F = faces.shape[:2]
+        faces = faces.view(B, F, 9)
+        tex = textures.detach().to(device=faces.device, dtype=torch.float32).contiguous().view(B, F, -1, 3)
+        S = int(image_size)
+        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=faces.device)
+        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=faces.device)
+        workspace = _ext.workspace_for(faces)
+        with torch.cuda.device(faces.device):
+            _ext.forward_render_raw(faces, tex, None, aggrs_info, soft_colors, params, False, workspace)
+        ctx.params = params
+        ctx.shapes = (face_vertices.shape, textures.shape)
+        ctx.save_for_backward(faces, tex, soft_colors, aggrs_info, workspace)
+        return soft_colors
+
+    @staticmethod
+    def backward(ctx, grad_soft_colors):
+        faces, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        grad_soft_colors = grad_soft_colors.to(torch.float32).contiguous()
+        want_tex = ctx.needs_input_grad[1]
+        grad_faces = torch.empty_like(faces)
+        grad_tex = torch.empty_like(tex) if want_tex else None
+        with torch.cuda.device(faces.device):
+            _ext.backward_render_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
+                                     ctx.params, workspace, True, True)
+        fshape, tshape = ctx.shapes
+        return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 17
+
+
+def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
+           dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
+           aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
+           aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
+           near=1, far=100, double_side=True, texture_type='surface'):
+    """face_vertices [B,F,3,3] (screen space), textures [B,F,T,3] -> RGBA images [B,4,S,S].
+    Keyword surface and defaults of gendr.functional.render (functional/renderer.py:239-262)."""
+    return GenDRFunction.apply(face_vertices, textures, image_size, background_color, dist_func, dist_scale,
+                               dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
+                               aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type)

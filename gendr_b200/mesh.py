@@ -1,0 +1,76 @@
+"""`Mesh` container: vertices [B,V,3], faces [B,F,3] int, textures [B,F,R*R,3] (surface) or [B,V,3] (vertex).
+API mirror of gendr.Mesh (/root/reference/gendr/mesh.py:14-126) minus OBJ texture I/O and voxelisation (asset
+pipeline / evaluation-only, out of the hot-path scope).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import functional
+
+
+def _default_device():
+    return torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
+
+
+class Mesh(object):
+    def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type='surface'):
+        if isinstance(vertices, np.ndarray):
+            vertices = torch.from_numpy(vertices).float().to(_default_device())
+        if isinstance(faces, np.ndarray):
+            faces = torch.from_numpy(faces).int().to(_default_device())
+        self._vertices = vertices[None] if vertices.ndimension() == 2 else vertices
+        self._faces = faces[None] if faces.ndimension() == 2 else faces
+        self.device = self._vertices.device
+        self.texture_type = texture_type
+        self.batch_size, self.num_vertices = self._vertices.shape[:2]
+        self.num_faces = self._faces.shape[1]
+
+        if textures is None:
+            if texture_type == 'surface':
+                shape, self.texture_res = (self.batch_size, self.num_faces, texture_res ** 2, 3), texture_res
+            elif texture_type == 'vertex':
+                shape, self.texture_res = (self.batch_size, self.num_vertices, 3), 1
+            else:
+                raise ValueError('texture type not applicable')
+            self._textures = torch.ones(*shape, dtype=torch.float32, device=self.device)
+        else:
+            if isinstance(textures, np.ndarray):
+                textures = torch.from_numpy(textures).float().to(self.device)
+            if textures.ndimension() == 3 and texture_type == 'surface':
+                textures = textures[None]
+            if textures.ndimension() == 2 and texture_type == 'vertex':
+                textures = textures[None]
+            self._textures = textures
+            self.texture_res = int(np.sqrt(self._textures.shape[2]))
+
+    @classmethod
+    def from_obj(cls, filename_obj, normalization=False, texture_res=1, texture_type='surface'):
+        vertices, faces = functional.load_obj(filename_obj, normalization=normalization)
+        dev = _default_device()
+        return cls(vertices.to(dev), faces.to(dev), None, texture_res, texture_type)
+
+    faces = property(lambda self: self._faces)
+    vertices = property(lambda self: self._vertices)
+    textures = property(lambda self: self._textures)
+
+    @property
+    def face_vertices(self):
+        return functional.face_vertices(self.vertices, self.faces)
+
+    @property
+    def surface_normals(self):
+        fv = self.face_vertices
+        return F.normalize(torch.cross(fv[:, :, 2] - fv[:, :, 1], fv[:, :, 0] - fv[:, :, 1], dim=2), p=2, dim=2, eps=1e-6)
+
+    @property
+    def vertex_normals(self):
+        return functional.vertex_normals(self.vertices, self.faces)
+
+    @property
+    def face_textures(self):
+        if self.texture_type == 'surface':
+            return self.textures
+        if self.texture_type == 'vertex':
+            return functional.face_vertices(self.textures, self.faces)
+        raise ValueError('texture type not applicable')

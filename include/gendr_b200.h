@@ -1,0 +1,102 @@
+/* gendr_b200.h -- C ABI of the B200-native GenDR soft rasterizer (libgendr_b200.so).
+ *
+ * Drop-in boundary.  These entry points are what the reference's Python binding for the hot path binds today via
+ * pybind11 (module `gendr.cuda.generalized_renderer`, /root/reference/gendr/cuda/generalized_renderer_cuda.cpp):
+ *
+ *   gendr_forward_render    replaces  forward_render   (generalized_renderer_cuda.cpp:74-127  -> K.cu:1071-1152)
+ *   gendr_backward_render   replaces  backward_render  (generalized_renderer_cuda.cpp:130-192 -> K.cu:1155-1227)
+ *   gendr_sigmoid_forward / gendr_sigmoid_backward / gendr_t_conorm_forward / gendr_t_conorm_backward
+ *                           replace   sigmoid_forward ... t_conorm_backward (generalized_renderer_cuda.cpp:195-236)
+ *
+ * Plain pointers and sizes only; no torch types.  All device pointers are fp32, contiguous, on ONE device (the
+ * library switches to the device that owns `faces`); work is enqueued on `stream` (a cudaStream_t passed as
+ * void*, NULL = legacy default stream) and nothing synchronises.  Return value: 0 on success, otherwise a
+ * cudaError_t (or GENDR_ERR_*); gendr_last_error() gives the text.  Unlike the reference (which only printf()s
+ * launch errors, K.cu:1111-1113) errors are reported to the caller.
+ *
+ * Buffer conventions are the reference's (gendr/functional/renderer.py:130-151, :191-197):
+ *   faces        [B,F,3,3]  screen-space (x,y in NDC [-1,1], z = depth) vertices of every face
+ *   textures     [B,F,T,3]  T = texture_res^2 texels (surface) or T = 3 vertex colours (vertex)
+ *   soft_colors  [B,4,S,S]  planar RGBA output
+ *   aggrs_info   [B,2,S,S]  softmax (sum,max) or hard (depth_min, face_index_min)
+ *   faces_info   [B,F,27]   optional: the reference's per-face scratch (inv 9 | gram 9 | obtuse 3 | 6 unused)
+ *   grad_faces   [B,F,3,3], grad_textures [B,F,T,3], grad_soft_colors [B,4,S,S]
+ */
+#ifndef GENDR_B200_H
+#define GENDR_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GENDR_ERR_INVALID_ARGUMENT 100001
+#define GENDR_ERR_WORKSPACE_TOO_SMALL 100002
+
+/* The 16 scalars of forward_render/backward_render (generalized_renderer_cuda.cpp:80-95), plus the background
+ * colour that the reference passes pre-filled inside soft_colors (functional/renderer.py:149-151). */
+typedef struct gendr_render_params {
+    int   image_size;
+    int   dist_func;              /* 0..17, functional/renderer.py:44-63 */
+    float dist_scale;
+    int   dist_squared;
+    float dist_shape;
+    float dist_shift;
+    float dist_eps;
+    int   aggr_alpha_func;        /* 0..9, functional/renderer.py:68-79 */
+    float aggr_alpha_t_conorm_p;
+    int   aggr_rgb_func;          /* 0 hard, 1 softmax */
+    float aggr_rgb_eps;
+    float aggr_rgb_gamma;
+    float near_plane;
+    float far_plane;
+    int   double_side;
+    int   texture_type;           /* 0 surface, 1 vertex */
+    float background[3];
+} gendr_render_params;
+
+/* Scratch the library needs between forward and backward: per-face records (144 B) + packed pixel rects (8 B). */
+size_t gendr_workspace_bytes(int batch, int faces);
+
+/* Forward.  background_prefilled != 0: read the background from soft_colors' RGB planes exactly as the reference
+ * does; 0: use params->background and treat soft_colors as uninitialised output.  faces_info may be NULL. */
+int gendr_forward_render(const float* faces, const float* textures, float* faces_info, float* aggrs_info,
+                         float* soft_colors, int batch, int num_faces, int texture_size,
+                         const gendr_render_params* params, int background_prefilled,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward.  workspace_valid != 0: the workspace still holds what gendr_forward_render left there for the same
+ * faces/params (skips re-running the face preprocessing).  zero_grads != 0: the library zero-fills grad_faces /
+ * grad_textures first (the reference expects the caller to pass zeros).  grad_textures may be NULL. */
+int gendr_backward_render(const float* faces, const float* textures, const float* soft_colors,
+                          const float* aggrs_info, float* grad_faces, float* grad_textures,
+                          const float* grad_soft_colors, int batch, int num_faces, int texture_size,
+                          const gendr_render_params* params, int workspace_valid, int zero_grads,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* End-to-end convenience with HOST buffers (pinned or pageable): H2D copies of faces/textures/grad_soft_colors,
+ * forward + backward on the current device, D2H copies of soft_colors/grad_faces/grad_textures, one stream
+ * synchronisation at the end.  Device scratch is cached inside the library between calls. */
+int gendr_render_forward_backward_host(const float* h_faces, const float* h_textures, const float* h_grad_soft_colors,
+                                       float* h_soft_colors, float* h_grad_faces, float* h_grad_textures,
+                                       int batch, int num_faces, int texture_size, const gendr_render_params* params);
+
+/* Scalar functions of the reference module (evaluated by the same device code the kernels use). */
+float gendr_sigmoid_forward(int function_id, float sign, float x, float scale, float dist_shape, float dist_shift);
+float gendr_sigmoid_backward(int function_id, float sign, float x, float scale, float dist_shape, float dist_shift);
+float gendr_t_conorm_forward(int t_conorm_id, float a_existing, float b_new, int face_id, float t_conorm_p);
+float gendr_t_conorm_backward(int t_conorm_id, float a_all, float b_current, int number_of_faces, float t_conorm_p);
+
+/* Diagnostics. */
+const char* gendr_last_error(void);
+const char* gendr_version(void);
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+long long gendr_launch_count(void);
+/* geometry probe: one thread evaluates prep + barycentric + projection for n (face, pixel) pairs.
+ * faces [n,9], xy [n,2] -> out [n,10] = w0 w1 w2 t0 t1 t2 dx dy sign d2   (device pointers) */
+int gendr_probe_pairs(const float* faces, const float* xy, float* out, int n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENDR_B200_H */
