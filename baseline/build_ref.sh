@@ -25,4 +25,8 @@ setup(name='gendr_ref_renderer',
       cmdclass={'build_ext': BuildExtension})
 PY
 TORCH_CUDA_ARCH_LIST="10.0a" MAX_JOBS=8 python setup_renderer_only.py build_ext --inplace > build.log 2>&1 || { tail -30 build.log; exit 1; }
+# the three off-path extensions (texture asset I/O, voxelizer) are not built: empty stand-ins so `import gendr` works
+for m in load_textures create_texture_image voxelization; do
+  [ -f gendr/cuda/$m.py ] || echo "# stand-in: extension not built (off the hot path)" > gendr/cuda/$m.py
+done
 ls -la gendr/cuda/*.so
