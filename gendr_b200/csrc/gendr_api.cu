@@ -160,7 +160,7 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
 // ---- scalar functions: one device thread, same templates as the render kernels --------------------------------
 template <int D> struct DistEval {
     static __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P) {
-        if (id == D) return pdf ? dist_pdf<D>(s, x, P) : dist_cdf<D>(s, x, P);
+        if (id == D) return pdf ? dist_pdf<D>(s, x, P) : (P.aggr_alpha_func == T_MAX ? dist_cdf<D, true, false>(s, x, P) : dist_cdf<D, false, false>(s, x, P));
         return DistEval<D + 1>::run(id, pdf, s, x, P);
     }
 };
@@ -247,7 +247,7 @@ int gendr_forward_render(const float* faces, const float* textures, float* faces
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_forward_render");
     if (batch == 0) return 0;
-    if (!faces || !textures || !aggrs_info || !soft_colors || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render");
+    if (((!faces || !textures) && num_faces > 0) || !aggrs_info || !soft_colors || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
     DeviceScope dev;
     GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");

@@ -53,7 +53,8 @@ class GenDRFunction(Function):
         faces = face_vertices.detach().to(torch.float32).contiguous()
         B, F = faces.shape[:2]
         faces = faces.view(B, F, 9)
-        tex = textures.detach().to(device=faces.device, dtype=torch.float32).contiguous().view(B, F, -1, 3)
+        tex = textures.detach().to(device=faces.device, dtype=torch.float32).contiguous()
+        tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
         S = int(image_size)
         soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=faces.device)
         aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=faces.device)
