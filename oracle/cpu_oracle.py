@@ -120,7 +120,8 @@ class Oracle:
         """-> dict(soft_colors [B,4,S,S], aggrs_info [B,2,S,S], faces_info [B,F,27], faces, textures)."""
         faces = np.ascontiguousarray(face_vertices, dtype=dtype).reshape(face_vertices.shape[0], -1, 9)
         B, F = faces.shape[:2]
-        tex = np.ascontiguousarray(textures, dtype=dtype).reshape(B, F, -1, 3)
+        tex = np.ascontiguousarray(textures, dtype=dtype)
+        tex = tex.reshape(B, F, -1, 3) if tex.size else np.zeros((B, F, 1, 3), dtype=dtype)
         Tn = tex.shape[2]
         # pad one face worth of texels: the reference reads texel R*R of face fn (= texel 0 of face fn+1),
         # SURVEY Q3; for the very last face that read is out of bounds in the reference (UB) -> define as 0.

@@ -1,0 +1,117 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/gendr_b200.h declares, the
+Python mirror keeps the reference's surface (names, defaults, id maps, validation), and the product refuses to run
+without CUDA (no fallback).  No compute calls are made here."""
+import ctypes as C
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+import gendr_b200 as gd
+from gendr_b200 import _lib
+from gendr_b200.functional import renderer as fr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, 'include', 'gendr_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(gendr_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    lib = C.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), 'missing export ' + n
+    assert sorted(_lib.SIGNATURES) == names, 'python binding table and header disagree'
+    lib.gendr_version.restype = C.c_char_p
+    assert b'sm_100a' in lib.gendr_version()
+    lib.gendr_workspace_bytes.restype = C.c_size_t
+    assert lib.gendr_workspace_bytes(64, 8192) >= 64 * 8192 * (144 + 8)
+
+
+def test_params_struct_layout_matches_header():
+    text = open(os.path.join(ROOT, 'include', 'gendr_b200.h')).read()
+    body = re.search(r'typedef struct gendr_render_params \{(.*?)\} gendr_render_params;', text, flags=re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = [(t, n) for t, n in re.findall(r'\b(int|float)\s+([a-z_]+)(?:\[3\])?;', body)]
+    py = [(('int' if f[1] is C.c_int else 'float'), f[0]) for f in _lib.RenderParams._fields_]
+    assert fields == py
+    assert C.sizeof(_lib.RenderParams) == 19 * 4
+
+
+def test_id_maps_are_the_references():
+    # gendr/functional/renderer.py:44-83
+    assert fr.DIST_FUNC_IDS == {'hard': 0, 'heaviside': 0, 'uniform': 1, 'cubic_hermite': 2, 'wigner_semicircle': 3, 'gaussian': 4,
+                                'laplace': 5, 'logistic': 6, 'gudermannian': 7, 'hyperbolic_secant': 7, 'cauchy': 8, 'reciprocal': 9,
+                                'gumbel_max': 10, 'gumbel_min': 11, 'exponential': 12, 'exponential_rev': 13, 'gamma': 14,
+                                'gamma_rev': 15, 'levy': 16, 'levy_rev': 17}
+    assert fr.AGGR_ALPHA_FUNC_IDS == {'hard': 0, 'max': 1, 'probabilistic': 2, 'einstein': 3, 'hamacher': 4, 'frank': 5, 'yager': 6,
+                                      'aczel_alsina': 7, 'dombi': 8, 'schweizer_sklar': 9}
+    assert fr.AGGR_RGB_FUNC_IDS == {'hard': 0, 'softmax': 1} and fr.TEXTURE_TYPE_IDS == {'surface': 0, 'vertex': 1}
+
+
+def test_gendr_module_surface():
+    sig = inspect.signature(gd.GenDR.__init__)
+    want = dict(image_size=256, background_color=[0, 0, 0], anti_aliasing=False, dist_func='uniform', dist_scale=1e-2,
+                dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4, aggr_alpha_func='probabilistic',
+                aggr_alpha_t_conorm_p=None, aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3, near=1, far=100,
+                double_side=False, texture_type='surface')              # gendr/renderer.py:13-36
+    assert {k: v.default for k, v in sig.parameters.items() if k != 'self'} == want
+    r = gd.GenDR(dist_func='gaussian', dist_scale=0.03)
+    r.dist_scale = 0.5                                                  # attributes stay mutable between calls
+    assert r.dist_scale == 0.5 and r.dist_func == 'gaussian'
+    with pytest.raises(ValueError):
+        gd.GenDR(aggr_rgb_func='mean')
+    with pytest.raises(ValueError):
+        gd.GenDR(texture_type='volume')
+    rsig = inspect.signature(gd.functional.render)
+    assert rsig.parameters['double_side'].default is True               # functional/renderer.py:262
+    assert list(rsig.parameters)[:4] == ['face_vertices', 'textures', 'image_size', 'background_color']
+
+
+def test_no_cpu_fallback():
+    fv, ft = torch.zeros(1, 2, 3, 3), torch.zeros(1, 2, 1, 3)
+    with pytest.raises((TypeError, RuntimeError)):
+        gd.functional.render(fv, ft, image_size=8)
+    from gendr_b200.cuda import generalized_renderer as ext
+    with pytest.raises(RuntimeError):
+        ext.forward_render(fv.view(1, 2, 9), ft, torch.zeros(1, 2, 27), torch.zeros(1, 2, 8, 8), torch.ones(1, 4, 8, 8),
+                           8, 1, 1e-2, False, 0., 0., 1e4, 2, 0., 1, 1e-3, 1e-3, 1., 100., True, 0)
+    with pytest.raises(AssertionError):
+        gd.functional.render(fv.cuda() if torch.cuda.is_available() else fv, ft, image_size=8, dist_scale=-1.0)
+    for path in ('gendr_b200/_lib.py', 'gendr_b200/functional/renderer.py', 'gendr_b200/cuda/generalized_renderer.py'):
+        src = open(os.path.join(ROOT, path)).read()
+        assert 'oracle' not in src.replace('# ', ''), path + ' must not reference the oracle'
+
+
+def test_mesh_camera_lighting_pipeline_on_cpu():
+    import scenes
+    verts, faces = scenes.icosphere(1)
+    assert verts.shape == (42, 3) and faces.shape == (80, 3)
+    mesh = gd.Mesh((verts * 0.5)[None].repeat(3, 1, 1), faces[None].repeat(3, 1, 1))
+    assert mesh.face_vertices.shape == (3, 80, 3, 3) and mesh.face_textures.shape == (3, 80, 1, 3)
+    lit = gd.Lighting()(mesh)
+    assert float(lit.textures.min()) >= 0.5 - 1e-6 and float(lit.textures.max()) <= 1.0 + 1e-6
+    cam = gd.LookAt(viewing_angle=15)
+    cam.set_eyes_from_angles(torch.full((3,), 2.732), torch.full((3,), 30.), torch.tensor([0., 120., 240.]))
+    out = cam(lit)
+    z = out.vertices[..., 2]
+    assert float(z.min()) > 1.0 and float(out.vertices[..., :2].abs().max()) < 1.0
+    vm = gd.Mesh(verts, faces, texture_type='vertex')
+    assert vm.face_textures.shape == (1, 80, 3, 3) and gd.Lighting()(vm).textures.shape == (1, 42, 3)
+    eye = gd.functional.get_points_from_angles(2., 0, 0)
+    assert abs(eye[2] + 2.0) < 1e-6 and abs(eye[0]) < 1e-6
+    v2 = gd.functional.look_at(torch.zeros(1, 1, 3), eye)
+    assert torch.allclose(v2, torch.tensor([[[0., 0., 2.]]]), atol=1e-6)
+    fv, ft, cfg = scenes.config_c1()
+    want = torch.tensor([[0, 0.2693377435, 2], [-0.3110042512, -0.2693377435, 2], [0.3110042512, -0.2693377435, 2]])
+    assert torch.allclose(fv[0, 0], want, atol=1e-6) and torch.allclose(ft, torch.full_like(ft, 0.5))
