@@ -39,6 +39,7 @@ SIGNATURES = {
     'gendr_version': (C.c_char_p, []),
     'gendr_launch_count': (C.c_longlong, []),
     'gendr_probe_pairs': (_I, [_P, _P, _P, _I, _P]),
+    'gendr_selftest_division': (C.c_longlong, [C.c_longlong]),
 }
 
 _lib = None

@@ -98,6 +98,7 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     if (u->dist_squared) r = std::sqrt(r);
     if (!(u->dist_scale > 0.f) || !(r == r)) r = std::numeric_limits<double>::infinity();
     P.cull_radius = (float)r;
+    P.cull_d2 = (float)((r * 1.01) * (r * 1.01) * 1.0001);
     P.gamma_kummer0 = (float)(1. / std::tgamma((double)u->dist_shape + 1.));
     P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
@@ -110,7 +111,7 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
 static size_t smem_bytes(const RenderParams& P) {
     const int n_sc = P.super_chunk;
     const int Fw = ((n_sc + NWARPS - 1) / NWARPS + 31) & ~31;
-    return (size_t)2 * STAGE_FACES * REC_WORDS * 4 + 2 * STAGE_FACES * 4 + 2 * 8 + 12 * 4 + (size_t)NWARPS * Fw * 2;
+    return smem_fixed_bytes() + (size_t)NWARPS * Fw * 2;
 }
 
 struct DeviceScope {   // run on the device that owns the data, restore the caller's device afterwards
@@ -159,18 +160,19 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
 
 // ---- scalar functions: one device thread, same templates as the render kernels --------------------------------
 template <int D> struct DistEval {
-    static __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P) {
-        if (id == D) return pdf ? dist_pdf<D>(s, x, P) : (P.aggr_alpha_func == T_MAX ? dist_cdf<D, true, false>(s, x, P) : dist_cdf<D, false, false>(s, x, P));
-        return DistEval<D + 1>::run(id, pdf, s, x, P);
+    static __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P, const Consts& K) {
+        if (id == D) return pdf ? dist_pdf<D>(s, x, P, K) : (P.aggr_alpha_func == T_MAX ? dist_cdf<D, true, false>(s, x, P, K) : dist_cdf<D, false, false>(s, x, P, K));
+        return DistEval<D + 1>::run(id, pdf, s, x, P, K);
     }
 };
 template <> struct DistEval<D_COUNT> {
-    static __device__ float run(int, bool, float, float, const RenderParams&) { return CUDART_NAN_F; }
+    static __device__ float run(int, bool, float, float, const RenderParams&, const Consts&) { return CUDART_NAN_F; }
 };
 __global__ void scalar_kernel(const __grid_constant__ RenderParams P, int what, int id, float a, float b, float* out) {
     float r;
-    if (what == 0) r = DistEval<0>::run(id, false, a, b, P);
-    else if (what == 1) r = DistEval<0>::run(id, true, a, b, P);
+    const Consts K = make_consts(P);
+    if (what == 0) r = DistEval<0>::run(id, false, a, b, P, K);
+    else if (what == 1) r = DistEval<0>::run(id, true, a, b, P, K);
     else if (what == 2) r = (id >= T_HAMACHER) ? tconorm_fold<true>(id, a, b, P) : tconorm_fold<false>(id, a, b, P);
     else r = (id >= T_HAMACHER) ? tconorm_dS<true>(id, a, b, P) : tconorm_dS<false>(id, a, b, P);
     *out = r;
@@ -211,6 +213,23 @@ __global__ void probe_kernel(const __grid_constant__ RenderParams P, const float
     float* o = out + (size_t)i * 10;
     o[0] = g.w0; o[1] = g.w1; o[2] = g.w2; o[3] = g.t0; o[4] = g.t1; o[5] = g.t2; o[6] = g.dx; o[7] = g.dy; o[8] = g.sign;
     o[9] = sop2(g.dx, g.dx, g.dy, g.dy);
+}
+
+// ---- self-test: div_exact (shared-reciprocal division) must be bit-identical to __fdiv_rn ---------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void division_selftest_kernel(unsigned long long n, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t h1 = mix32((uint32_t)i * 2u + 1u), h2 = mix32((uint32_t)(i >> 7) * 2654435761u + 12345u);
+        // divisor: random mantissa, exponent in [2^-20, 2^20], random sign; dividend: exponent in [2^-40, 2^20] or zero
+        const float b = __uint_as_float((h1 & 0x807fffffu) | ((107u + (h1 >> 23) % 41u) << 23));
+        float a = __uint_as_float((h2 & 0x807fffffu) | ((87u + (h2 >> 23) % 61u) << 23));
+        if ((h2 & 0xff) == 0) a = 0.f;
+        const Rcp r = make_rcp(b);
+        const float q1 = div_exact(a, r), q2 = __fdiv_rn(a, b);
+        if (__float_as_uint(q1) != __float_as_uint(q2)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // ---- cached device scratch for the host-buffer entry point -----------------------------------------------------
@@ -349,6 +368,19 @@ float gendr_t_conorm_forward(int id, float a_existing, float b_new, int face_id,
 float gendr_t_conorm_backward(int id, float a_all, float b_current, int number_of_faces, float p) {
     (void)number_of_faces;
     return run_scalar(3, id, a_all, b_current, 1.f, 0.f, 0.f, p);
+}
+
+long long gendr_selftest_division(long long n) {
+    unsigned long long* d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) return -1;
+    cudaMemset(d, 0, sizeof(unsigned long long));
+    division_selftest_kernel<<<148 * 8, 256>>>((unsigned long long)n, d);
+    g_launches++;
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { fail((int)e, "division self-test"); return -1; }
+    return (long long)h;
 }
 
 int gendr_probe_pairs(const float* faces, const float* xy, float* out, int n, void* stream) {

@@ -92,6 +92,9 @@ const char* gendr_last_error(void);
 const char* gendr_version(void);
 /* number of kernels this library has launched since load (bench.py's "gpu_launches") */
 long long gendr_launch_count(void);
+/* self-test: number of (dividend, divisor) pairs out of n pseudo-random ones for which the library's shared-reciprocal
+ * division differs from IEEE division by a single bit (must be 0); -1 on CUDA error */
+long long gendr_selftest_division(long long n);
 /* geometry probe: one thread evaluates prep + barycentric + projection for n (face, pixel) pairs.
  * faces [n,9], xy [n,2] -> out [n,10] = w0 w1 w2 t0 t1 t2 dx dy sign d2   (device pointers) */
 int gendr_probe_pairs(const float* faces, const float* xy, float* out, int n, void* stream);

@@ -129,6 +129,13 @@ def test_known_answers_survey(port_oracle):
         assert abs(ext.sigmoid_backward(did, 1., .01, .1, 1., 0.) - pdf) < 2e-5
 
 
+def test_shared_reciprocal_division_is_ieee_exact():
+    """div_exact() (one MUFU.RCP + Newton shared by several quotients) must equal __fdiv_rn bit for bit."""
+    _dev()
+    from gendr_b200 import _lib
+    assert _lib.load().gendr_selftest_division(400_000_000) == 0
+
+
 # ---- geometry: bit-identical to the oracle's GPU-contraction arithmetic, slivers included ----------------------
 def test_pair_geometry_bitwise(gpu_oracle):
     dev = _dev()
