@@ -79,7 +79,7 @@ static double cull_x_over_tau(int dist, double shift) {
 
 static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_params* u) {
     if (!u) return GENDR_ERR_INVALID_ARGUMENT;
-    if (B < 0 || F < 0 || T < 1 || u->image_size < 1 || u->image_size > 32767) return GENDR_ERR_INVALID_ARGUMENT;
+    if (B < 0 || F < 0 || T < 1 || u->image_size < 1 || u->image_size > 16383) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->dist_func < 0 || u->dist_func >= D_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->aggr_alpha_func < 0 || u->aggr_alpha_func >= T_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
     memset(&P, 0, sizeof P);
