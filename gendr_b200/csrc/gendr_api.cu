@@ -80,6 +80,7 @@ static double cull_x_over_tau(int dist, double shift) {
 static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_params* u) {
     if (!u) return GENDR_ERR_INVALID_ARGUMENT;
     if (B < 0 || F < 0 || T < 1 || u->image_size < 1 || u->image_size > 16383) return GENDR_ERR_INVALID_ARGUMENT;
+    if ((long long)B * F >= (1ll << 31) || (long long)B * u->image_size * u->image_size >= (1ll << 31)) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->dist_func < 0 || u->dist_func >= D_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->aggr_alpha_func < 0 || u->aggr_alpha_func >= T_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
     memset(&P, 0, sizeof P);
@@ -238,7 +239,10 @@ struct HostPathScratch {
     int device = -1;
     size_t cap = 0;
     char* base = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                 // compute
+    cudaStream_t h2d = nullptr, d2h = nullptr;     // copy engines, overlapped with the kernels
+    static const int MAX_CHUNKS = 8;
+    cudaEvent_t in_ready[MAX_CHUNKS] = {}, done[MAX_CHUNKS] = {};
 };
 static HostPathScratch g_scratch;
 
@@ -257,6 +261,39 @@ size_t gendr_workspace_bytes(int batch, int faces) {
     size_t rec = ((size_t)batch * faces * REC_BYTES + 255) & ~(size_t)255;
     size_t rct = ((size_t)batch * faces * sizeof(uint2) + 255) & ~(size_t)255;
     return rec + rct + 256;
+}
+
+static int gendr_forward_render_chunk(const float* faces, const float* textures, long long tex_elems, float* aggrs_info, float* soft_colors,
+                                      int batch, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
+                                      size_t workspace_bytes, cudaStream_t st) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_render_forward_backward_host");
+    (void)workspace_bytes;
+    if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = tex_elems;
+    io.soft_colors = soft_colors; io.aggrs = aggrs_info; io.bg_from_buffer = 0;
+    return run_render(P, io, false, st);
+}
+
+static int gendr_backward_render_chunk(const float* faces, const float* textures, long long tex_elems, const float* soft_colors,
+                                       const float* aggrs_info, float* grad_faces, float* grad_textures, const float* grad_soft_colors,
+                                       int batch, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
+                                       size_t workspace_bytes, cudaStream_t st) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_render_forward_backward_host");
+    (void)workspace_bytes; (void)faces;
+    GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
+    if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = tex_elems;
+    io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
+    io.grad_colors = grad_soft_colors; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
+    return run_render(P, io, true, st);
 }
 
 int gendr_forward_render(const float* faces, const float* textures, float* faces_info, float* aggrs_info,
@@ -312,9 +349,12 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
                                        float* h_soft_colors, float* h_grad_faces, float* h_grad_textures,
                                        int batch, int num_faces, int texture_size, const gendr_render_params* params) {
     if (!params || !h_faces || !h_textures || !h_soft_colors) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_render_forward_backward_host");
+    if (batch <= 0) return 0;
     const size_t S = (size_t)params->image_size;
-    const size_t n_faces = (size_t)batch * num_faces * 9 * 4, n_tex = (size_t)batch * num_faces * texture_size * 3 * 4;
-    const size_t n_col = (size_t)batch * 4 * S * S * 4, n_agg = (size_t)batch * 2 * S * S * 4;
+    // per batch item
+    const size_t e_faces = (size_t)num_faces * 9, e_tex = (size_t)num_faces * texture_size * 3, e_col = 4 * S * S, e_agg = 2 * S * S;
+    const size_t n_faces = (size_t)batch * e_faces * 4, n_tex = (size_t)batch * e_tex * 4;
+    const size_t n_col = (size_t)batch * e_col * 4, n_agg = (size_t)batch * e_agg * 4;
     const size_t n_ws = gendr_workspace_bytes(batch, num_faces);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const bool bwd = h_grad_soft_colors && h_grad_faces;
@@ -322,13 +362,21 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     std::lock_guard<std::mutex> lock(g_scratch.mu);
     int dev = 0;
     GENDR_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
+    if (g_scratch.device != dev || !g_scratch.stream) {
+        GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.h2d, cudaStreamNonBlocking), "cudaStreamCreate");
+        GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.d2h, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < HostPathScratch::MAX_CHUNKS; ++i) {
+            GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.in_ready[i], cudaEventDisableTiming), "cudaEventCreate");
+            GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.done[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+    }
     if (g_scratch.device != dev || g_scratch.cap < need) {
         if (g_scratch.base) { cudaSetDevice(g_scratch.device); cudaFree(g_scratch.base); cudaSetDevice(dev); g_scratch.base = nullptr; g_scratch.cap = 0; }
-        if (!g_scratch.stream || g_scratch.device != dev) GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaMalloc(&g_scratch.base, need), "cudaMalloc of host-path scratch");
-        g_scratch.cap = need; g_scratch.device = dev;
+        g_scratch.cap = need;
     }
-    cudaStream_t st = g_scratch.stream;
+    g_scratch.device = dev;
     char* p = g_scratch.base;
     float* d_faces = (float*)p; p += al(n_faces);
     float* d_gfaces = (float*)p; p += al(n_faces);
@@ -338,20 +386,33 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     float* d_gcol = (float*)p; p += al(n_col);
     float* d_agg = (float*)p; p += al(n_agg);
     void* d_ws = p;
-    GENDR_CUDA(cudaMemcpyAsync(d_faces, h_faces, n_faces, cudaMemcpyHostToDevice, st), "H2D faces");
-    GENDR_CUDA(cudaMemcpyAsync(d_tex, h_textures, n_tex, cudaMemcpyHostToDevice, st), "H2D textures");
-    if (bwd) GENDR_CUDA(cudaMemcpyAsync(d_gcol, h_grad_soft_colors, n_col, cudaMemcpyHostToDevice, st), "H2D grad_soft_colors");
-    if (int e = gendr_forward_render(d_faces, d_tex, nullptr, d_agg, d_col, batch, num_faces, texture_size, params, 0, d_ws, n_ws, st)) return e;
+    // Three streams: uploads / compute / downloads.  The cotangent upload (the largest input) overlaps the forward
+    // kernel, the image download overlaps the backward kernel; kernels always see the full batch (full-size grids).
+    GENDR_CUDA(cudaMemcpyAsync(d_tex, h_textures, n_tex, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D textures");
+    GENDR_CUDA(cudaMemcpyAsync(d_faces, h_faces, n_faces, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D faces");
+    GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[0], g_scratch.h2d), "event record");
     if (bwd) {
-        if (int e = gendr_backward_render(d_faces, d_tex, d_col, d_agg, d_gfaces, h_grad_textures ? d_gtex : nullptr, d_gcol, batch, num_faces,
-                                          texture_size, params, 1, 1, d_ws, n_ws, st)) return e;
+        GENDR_CUDA(cudaMemcpyAsync(d_gcol, h_grad_soft_colors, n_col, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D grad_soft_colors");
+        GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[1], g_scratch.h2d), "event record");
     }
-    GENDR_CUDA(cudaMemcpyAsync(h_soft_colors, d_col, n_col, cudaMemcpyDeviceToHost, st), "D2H soft_colors");
+    GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[0], 0), "stream wait");
+    if (int e = gendr_forward_render_chunk(d_faces, d_tex, (long long)batch * (long long)e_tex, d_agg, d_col, batch, num_faces, texture_size,
+                                           params, d_ws, n_ws, g_scratch.stream)) return e;
+    GENDR_CUDA(cudaEventRecord(g_scratch.done[0], g_scratch.stream), "event record");
+    GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[0], 0), "stream wait");
+    GENDR_CUDA(cudaMemcpyAsync(h_soft_colors, d_col, n_col, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H soft_colors");
     if (bwd) {
-        GENDR_CUDA(cudaMemcpyAsync(h_grad_faces, d_gfaces, n_faces, cudaMemcpyDeviceToHost, st), "D2H grad_faces");
-        if (h_grad_textures) GENDR_CUDA(cudaMemcpyAsync(h_grad_textures, d_gtex, n_tex, cudaMemcpyDeviceToHost, st), "D2H grad_textures");
+        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[1], 0), "stream wait");
+        if (int e = gendr_backward_render_chunk(d_faces, d_tex, (long long)batch * (long long)e_tex, d_col, d_agg, d_gfaces,
+                                                h_grad_textures ? d_gtex : nullptr, d_gcol, batch, num_faces, texture_size, params, d_ws, n_ws,
+                                                g_scratch.stream)) return e;
+        GENDR_CUDA(cudaEventRecord(g_scratch.done[1], g_scratch.stream), "event record");
+        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[1], 0), "stream wait");
+        GENDR_CUDA(cudaMemcpyAsync(h_grad_faces, d_gfaces, n_faces, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_faces");
+        if (h_grad_textures) GENDR_CUDA(cudaMemcpyAsync(h_grad_textures, d_gtex, n_tex, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_textures");
     }
-    GENDR_CUDA(cudaStreamSynchronize(st), "host-path stream synchronize");
+    GENDR_CUDA(cudaStreamSynchronize(g_scratch.d2h), "host-path stream synchronize");
+    GENDR_CUDA(cudaStreamSynchronize(g_scratch.stream), "host-path stream synchronize");
     return 0;
 }
 
