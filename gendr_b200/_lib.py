@@ -30,6 +30,8 @@ SIGNATURES = {
     'gendr_workspace_bytes': (_SZ, [_I, _I]),
     'gendr_forward_render': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _P, _SZ, _P]),
     'gendr_backward_render': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _I, _P, _SZ, _P]),
+    'gendr_forward_render_indexed': (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_backward_render_indexed': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _PP, _I, _P, _SZ, _P]),
     'gendr_render_forward_backward_host': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _PP]),
     'gendr_sigmoid_forward': (_F, [_I, _F, _F, _F, _F, _F]),
     'gendr_sigmoid_backward': (_F, [_I, _F, _F, _F, _F, _F]),

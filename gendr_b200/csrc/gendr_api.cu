@@ -39,6 +39,29 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Rende
     rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
 }
 
+// indexed variant: gathers the face's three vertices from vertices[B,V,3] through face_index (fused vertices[faces])
+__global__ void __launch_bounds__(256) prep_indexed_kernel(const __grid_constant__ RenderParams P, const float* __restrict__ vertices,
+                                                           const int* __restrict__ face_index, long long index_batch_stride, int V,
+                                                           float* __restrict__ records, uint2* __restrict__ rects) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)P.B * P.F) return;
+    const long long b = i / P.F, f = i - b * P.F;
+    float v[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int vi = __ldg(face_index + b * index_batch_stride + f * 3 + k);
+        vi = min(max(vi, 0), V - 1);
+        const float* src = vertices + (b * V + vi) * 3;
+        v[3 * k] = __ldg(src); v[3 * k + 1] = __ldg(src + 1); v[3 * k + 2] = __ldg(src + 2);
+    }
+    float rec[REC_WORDS];
+    prep_face_record(v, rec, nullptr, P);
+    float4* dst = reinterpret_cast<float4*>(records + i * REC_WORDS);
+#pragma unroll
+    for (int k = 0; k < REC_WORDS / 4; ++k) dst[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+    rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+}
+
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -414,6 +437,61 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.d2h), "host-path stream synchronize");
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.stream), "host-path stream synchronize");
     return 0;
+}
+
+int gendr_forward_render_indexed(const float* vertices, const int* face_index, int index_shared, const float* textures, float* aggrs_info,
+                                 float* soft_colors, int batch, int num_vertices, int num_faces, int texture_size,
+                                 const gendr_render_params* params, void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_forward_render_indexed");
+    if (batch == 0) return 0;
+    if (((!vertices || !face_index || !textures) && num_faces > 0) || !aggrs_info || !soft_colors || !workspace || num_vertices < 1)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render_indexed");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long n = (long long)batch * num_faces;
+    if (n > 0) {
+        prep_indexed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, vertices, face_index, index_shared ? 0 : (long long)num_faces * 3, num_vertices,
+                                                                       ws_records(workspace), ws_rects(workspace, batch, num_faces));
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "prep_indexed_kernel launch");
+    }
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
+    io.soft_colors = soft_colors; io.aggrs = aggrs_info;
+    return run_render(P, io, false, st);
+}
+
+int gendr_backward_render_indexed(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
+                                  const float* aggrs_info, float* grad_vertices, float* grad_textures, const float* grad_soft_colors,
+                                  int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
+                                  int zero_grads, void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_indexed");
+    if (batch == 0) return 0;
+    if (!face_index || !textures || !soft_colors || !aggrs_info || !grad_vertices || !grad_soft_colors || !workspace || num_vertices < 1)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(grad_vertices), "selecting the device that owns `grad_vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (zero_grads) {
+        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)batch * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
+        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
+    }
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);    // left there by the indexed forward
+    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
+    io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
+    io.grad_colors = grad_soft_colors; io.grad_textures = grad_textures;
+    io.grad_vertices = grad_vertices; io.face_index = face_index; io.index_batch_stride = index_shared ? 0 : (long long)num_faces * 3;
+    io.num_vertices = num_vertices;
+    return run_render(P, io, true, st);
 }
 
 float gendr_sigmoid_forward(int id, float sign, float x, float scale, float shape, float shift) {

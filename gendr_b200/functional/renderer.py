@@ -80,6 +80,74 @@ class GenDRFunction(Function):
         return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 17
 
 
+class GenDRIndexedFunction(Function):
+    """render() for an indexed mesh: (vertices [B,V,3] screen space, faces [B,F,3] or [F,3] int) instead of the gathered
+    face_vertices [B,F,3,3].  The gather runs inside the face preprocessing kernel and the gradient is scatter-added
+    into grad_vertices [B,V,3] by the backward kernel (replaces gendr/functional/face_vertices.py:27 and its
+    index_put backward)."""
+    @staticmethod
+    def forward(ctx, vertices, faces, textures, image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape,
+                dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma,
+                near, far, double_side, texture_type):
+        assert dist_scale >= 0, dist_scale
+        assert dist_eps >= 1, dist_eps
+        if not vertices.is_cuda:
+            raise TypeError('GenDR only supports CUDA Tensors.')
+        params = _ext.make_params(
+            image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
+            _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
+            _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
+            TEXTURE_TYPE_IDS[texture_type], background_color)
+        verts = vertices.detach().to(torch.float32).contiguous()
+        B, V = verts.shape[:2]
+        index = faces.detach().to(device=verts.device, dtype=torch.int32).contiguous()
+        shared = index.ndimension() == 2
+        F = index.shape[-2]
+        tex = textures.detach().to(device=verts.device, dtype=torch.float32).contiguous()
+        tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
+        S = int(image_size)
+        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=verts.device)
+        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=verts.device)
+        lib = _ext._lib.load()
+        workspace = torch.empty(lib.gendr_workspace_bytes(B, F), dtype=torch.uint8, device=verts.device)
+        with torch.cuda.device(verts.device):
+            _ext._lib.check(lib.gendr_forward_render_indexed(
+                verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
+                B, V, F, int(tex.shape[2]), params, workspace.data_ptr(), workspace.numel(),
+                torch.cuda.current_stream(verts.device).cuda_stream))
+        ctx.params, ctx.dims, ctx.shapes = params, (B, V, F, int(tex.shape[2]), shared), (vertices.shape, textures.shape)
+        ctx.save_for_backward(index, tex, soft_colors, aggrs_info, workspace)
+        return soft_colors
+
+    @staticmethod
+    def backward(ctx, grad_soft_colors):
+        index, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        B, V, F, T, shared = ctx.dims
+        grad_soft_colors = grad_soft_colors.to(torch.float32).contiguous()
+        want_tex = ctx.needs_input_grad[2]
+        grad_vertices = torch.empty((B, V, 3), dtype=torch.float32, device=tex.device)
+        grad_tex = torch.empty_like(tex) if want_tex else None
+        lib = _ext._lib.load()
+        with torch.cuda.device(tex.device):
+            _ext._lib.check(lib.gendr_backward_render_indexed(
+                index.data_ptr(), int(shared), tex.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
+                grad_vertices.data_ptr(), grad_tex.data_ptr() if want_tex else None, grad_soft_colors.data_ptr(), B, V, F, T,
+                ctx.params, 1, workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(tex.device).cuda_stream))
+        vshape, tshape = ctx.shapes
+        return (grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None) + (None,) * 17
+
+
+def render_indexed(vertices, faces, textures, image_size=256, background_color=[0, 0, 0],
+                   dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
+                   aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
+                   aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
+                   near=1, far=100, double_side=True, texture_type='surface'):
+    """Same as render(), for (vertices [B,V,3], faces [B,F,3] | [F,3]) instead of face_vertices [B,F,3,3]."""
+    return GenDRIndexedFunction.apply(vertices, faces, textures, image_size, background_color, dist_func, dist_scale,
+                                      dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
+                                      aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type)
+
+
 def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
            dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
            aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,

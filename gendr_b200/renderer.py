@@ -39,4 +39,10 @@ class GenDR(nn.Module):
         return images
 
     def forward(self, mesh):
+        if mesh.texture_type == 'surface' and getattr(self, 'fused_gather', True):
+            # indexed path: vertices[faces] gather and its scatter-add backward run inside the CUDA kernels
+            size = self.image_size * (2 if self.anti_aliasing else 1)
+            images = functional.render_indexed(mesh.vertices, mesh.faces, mesh.textures, image_size=size,
+                                               **{name: getattr(self, name) for name in _RENDER_ARGS})
+            return F.avg_pool2d(images, kernel_size=2, stride=2) if self.anti_aliasing else images
         return self.forward_tensors(mesh.face_vertices, mesh.face_textures)

@@ -74,6 +74,21 @@ int gendr_backward_render(const float* faces, const float* textures, const float
                           const gendr_render_params* params, int workspace_valid, int zero_grads,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Indexed-mesh variants: fuse the reference's `vertices[faces]` gather
+ * (gendr/functional/face_vertices.py:9-27, called from gendr/mesh.py:102) into the face preprocessing and its backward
+ * (a scatter-add into the vertex gradient) into the backward kernel, so the [B,F,3,3] face-vertex tensor and its
+ * gradient are never materialised.  vertices [B,V,3] screen space; face_index int32 [B,F,3], or [F,3] when
+ * index_shared != 0; indices are clamped to [0, V-1].  The backward must follow the forward on the same workspace. */
+int gendr_forward_render_indexed(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                 float* aggrs_info, float* soft_colors, int batch, int num_vertices, int num_faces,
+                                 int texture_size, const gendr_render_params* params, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int gendr_backward_render_indexed(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
+                                  const float* aggrs_info, float* grad_vertices, float* grad_textures,
+                                  const float* grad_soft_colors, int batch, int num_vertices, int num_faces,
+                                  int texture_size, const gendr_render_params* params, int zero_grads, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* End-to-end convenience with HOST buffers (pinned or pageable): H2D copies of faces/textures/grad_soft_colors,
  * forward + backward on the current device, D2H copies of soft_colors/grad_faces/grad_textures, one stream
  * synchronisation at the end.  Device scratch is cached inside the library between calls. */

@@ -391,3 +391,34 @@ def test_full_size_properties():
     perm = torch.randperm(64, generator=torch.Generator().manual_seed(0)).to(dev)
     assert torch.equal(gd.functional.render(fvs[perm].contiguous(), fts[perm].contiguous(), **kw), base[perm])
     assert torch.equal(base[:, 3], full[:, 3]), 'a face far off screen must not change alpha by a single bit'
+
+
+# ---- fused vertices[faces] gather / scatter-add ---------------------------------------------
+def test_indexed_mesh_path_equals_gather_then_render():
+    """render_indexed(vertices, faces) == render(vertices[faces]) bit for bit; grad_vertices equals the scatter-add of
+    grad_faces that torch's index backward produces (to atomic-order noise)."""
+    dev = _dev()
+    import gendr_b200 as gd
+    verts, faces = scenes.icosphere(3)
+    B = 3
+    mesh = gd.Mesh((verts * 0.5)[None].repeat(B, 1, 1).to(dev), faces[None].repeat(B, 1, 1).to(dev))
+    cam = gd.LookAt(viewing_angle=15)
+    cam.set_eyes(scenes.orbit_eyes(B).to(dev))
+    mesh = cam(gd.Lighting()(mesh))
+    g = torch.randn(B, 4, 96, 96, generator=torch.Generator().manual_seed(4)).to(dev)
+    kw = dict(image_size=96, dist_func='logistic', aggr_alpha_func='probabilistic', dist_scale=0.01, double_side=False)
+    v1 = mesh.vertices.detach().clone().requires_grad_(True)
+    t1 = mesh.textures.detach().clone().requires_grad_(True)
+    img1 = gd.functional.render(gd.functional.face_vertices(v1, mesh.faces), t1, **kw)
+    img1.backward(g)
+    for index in (mesh.faces, mesh.faces[0]):               # per-item [B,F,3] and batch-shared [F,3] index buffers
+        v2 = mesh.vertices.detach().clone().requires_grad_(True)
+        t2 = mesh.textures.detach().clone().requires_grad_(True)
+        img2 = gd.functional.render_indexed(v2, index, t2, **kw)
+        img2.backward(g)
+        assert torch.equal(img1, img2)
+        assert_close('indexed grad_vertices', v2.grad, v1.grad, atol=2e-5 * float(v1.grad.abs().max()), rtol=1e-5)
+        assert_close('indexed grad_textures', t2.grad, t1.grad, atol=2e-5 * float(t1.grad.abs().max()), rtol=1e-5)
+    # the module front door uses the fused path for surface textures and must agree with forward_tensors
+    r = gd.GenDR(**kw)
+    assert torch.equal(r(mesh), r.forward_tensors(mesh.face_vertices, mesh.face_textures))
