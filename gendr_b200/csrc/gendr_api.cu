@@ -127,7 +127,7 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
     P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
-    P.super_chunk = F < 8192 ? ((F + 255) / 256) * 256 : 8192;
+    P.super_chunk = F < 4096 ? ((F + 255) / 256) * 256 : 4096;     // index list of 8 KB next to the 44 KB wave buffer: 4 CTAs/SM
     if (P.super_chunk < 256) P.super_chunk = 256;
     return 0;
 }
