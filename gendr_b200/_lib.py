@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libgendr_b200.so')
+# GENDR_B200_LIB selects an alternative build of the same library (tuning experiments); default: the in-tree build
+LIB_PATH = os.environ.get('GENDR_B200_LIB') or os.path.join(_HERE, 'libgendr_b200.so')
 
 
 class RenderParams(C.Structure):
