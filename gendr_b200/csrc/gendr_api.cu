@@ -175,7 +175,9 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     cfg.smem = smem_bytes(P);
     cfg.stream = st;
     cfg.backward = backward;
-    cfg.parametric = P.aggr_alpha_func >= T_HAMACHER;
+    cfg.fast = (P.aggr_rgb_func == 1 && P.texture_type == 0 && !P.dist_squared &&
+                (P.aggr_alpha_func == T_PROBABILISTIC || P.aggr_alpha_func == T_EINSTEIN));
+    cfg.tcn_mode = cfg.fast ? P.aggr_alpha_func : (P.aggr_alpha_func >= T_HAMACHER ? 1 : 0);
     cudaError_t e = kLaunchTable[P.dist_func](P, io, cfg);
     g_launches++;
     if (e != cudaSuccess) return fail((int)e, backward ? "backward render_kernel launch" : "forward render_kernel launch");
