@@ -422,3 +422,55 @@ def test_indexed_mesh_path_equals_gather_then_render():
     # the module front door uses the fused path for surface textures and must agree with forward_tensors
     r = gd.GenDR(**kw)
     assert torch.equal(r(mesh), r.forward_tensors(mesh.face_vertices, mesh.face_textures))
+
+
+# ---- randomized configurations vs the CPU oracle ----------------------------------------------------------------
+def test_randomized_configurations(gpu_oracle):
+    """30 seeded random configurations (distribution, t-conorm, scale, shape/shift, dist_eps, near/far, sidedness, texture
+    type/resolution, RGB mode, image size, background) on a random soup with degenerate faces mixed in."""
+    dev = _dev()
+    rng = np.random.default_rng(2024)
+    gen = torch.Generator().manual_seed(7)
+    failures = []
+    for trial in range(30):
+        dist, dkw = scenes.DIST_SWEEP[int(rng.integers(0, 18))]
+        tname, tp = scenes.TCN_SWEEP[int(rng.integers(0, 10))]
+        S = int(rng.choice([17, 32, 40, 48, 61]))
+        F = int(rng.integers(20, 260))
+        B = int(rng.integers(1, 4))
+        fv, _ = scenes.soup(F, batch=B, seed=int(rng.integers(0, 10 ** 6)), size=float(rng.choice([0.05, 0.15, 0.4])))
+        if rng.random() < 0.5:
+            fv[0, 0] = fv[0, 0, 0]                                   # zero-area face
+            fv[0, 1, 2, :2] = 0.5 * (fv[0, 1, 0, :2] + fv[0, 1, 1, :2])   # collinear face
+        tex_type = 'vertex' if rng.random() < 0.25 else 'surface'
+        T = 3 if tex_type == 'vertex' else int(rng.choice([1, 1, 4, 9]))
+        ft = torch.rand(B, fv.shape[1], T, 3, generator=gen)
+        rgb = 'hard' if rng.random() < 0.3 else 'softmax'
+        squared = bool(rng.random() < 0.25)
+        kw = dict(image_size=S, dist_func=dist, aggr_alpha_func=tname, aggr_alpha_t_conorm_p=tp, aggr_rgb_func=rgb,
+                  dist_squared=squared, dist_scale=float(rng.choice([3e-4, 1e-3])) if squared else float(rng.choice([0.01, 0.03, 0.08])),
+                  dist_eps=float(rng.choice([1e4, 300., 20., 2.0])), near=float(rng.choice([1.0, 2.5])), far=float(rng.choice([100., 3.5])),
+                  double_side=bool(rng.random() < 0.5), texture_type=tex_type, background_color=[float(x) for x in rng.random(3)],
+                  aggr_rgb_gamma=float(rng.choice([1e-3, 1e-2, 0.5])), **dkw)
+        if dist in ('exponential', 'exponential_rev', 'gamma', 'gamma_rev', 'levy', 'levy_rev') and rng.random() < 0.5:
+            kw['dist_shift'] = float(rng.choice([-0.5, 0.5, 2.0]))
+        g = torch.randn(B, 4, S, S, generator=gen)
+        ill = (dist in TAIL_CANCELLING or dist == 'levy_rev') and rgb == 'softmax' and kw['aggr_rgb_gamma'] < 0.1
+        if ill:
+            g[:, :3] = 0          # see TAIL_CANCELLING above: only alpha is well conditioned against the CPU libm
+        try:
+            img, gf, gt = render_new(fv, ft, g, dev, **kw)
+            ime, gfe, gte = render_oracle(gpu_oracle, fv, ft, g, **kw)
+            assert_close('alpha', img[:, 3], ime[:, 3], atol=1e-5)
+            if not ill:
+                assert_close('rgb', img[:, :3], ime[:, :3], atol=1e-5)
+            # wigner + max: the reference's forward and backward kernels contract tau^2 - x^2 differently, so whether
+            # `a_all == b_current` (K.cu:575) holds depends on the last bit of asinf() -- libm and libdevice disagree
+            # there, only the reference's own CUDA kernels can arbitrate (test_reference_cuda_c5_sweep does)
+            chaotic = dist == 'levy_rev' or (dist == 'wigner_semicircle' and tname == 'max')
+            if not chaotic:
+                assert_close('grad_faces', gf, gfe, atol=1e-4 * float(gfe.abs().max()) + 1e-30)
+                assert_close('grad_textures', gt, gte, atol=1e-4 * float(gte.abs().max()) + 1e-30)
+        except AssertionError as e:
+            failures.append('trial %d %s: %s' % (trial, {k: v for k, v in kw.items() if k != 'background_color'}, str(e).splitlines()[0]))
+    assert not failures, '\n'.join(failures)
