@@ -16,7 +16,9 @@ pairs (culled pairs count, exactly as they do for the reference), whole job over
   cpu_baseline  rank 0, N = 1: the unmodified reference kernels run on the host cores through oracle/_ref (kind
                 "reference"), or the C port when that build is absent (kind "port"), on a bounded sample
   reference_cuda  (extra) the reference's own CUDA kernels (baseline/_ref, sm_100a build) on the same GPU, same inputs
-  --impl reference  times the reference's CPU path (oracle/_ref or the port) on the host cores, rank 0 only
+  --impl reference  rank 0 only: the unmodified reference (baseline/_ref) through gendr.functional.render on one B200 --
+                    GenDR's implementation of the path is its CUDA extension; there is no CPU rasterizer -- with the
+                    CPU-shim figure as `cpu_baseline`; CPU shim alone when no GPU / no reference build is present
 """
 import argparse
 import ctypes as C
@@ -133,6 +135,100 @@ def cpu_reference_arm(fv, ft, kw, steps, warmup, sample_size=128):
                 ms_per_step=1e3 * total / len(times))
 
 
+def reference_arm(args):
+    """`--impl reference`: the UNMODIFIED reference through its own public API (gendr.functional.render + backward) on the
+    same workload.  GenDR ships no CPU rasterizer -- its implementation of the path IS its CUDA extension -- so the arm runs
+    the reference's CUDA kernels (baseline/_ref, stock sources built for sm_100a) on one B200, which is the baseline
+    BASELINE.json's north star names.  `value`: inputs resident in HBM; `e2e`: pinned host buffers in, H2D + render +
+    backward + D2H of image and gradients inside the timed region.  `cpu_baseline` (always reported beside it): the
+    reference's kernels compiled for the host through oracle/ref_shim.h, timed on a bounded sample.  Without a GPU or
+    without baseline/_ref the CPU figure becomes the line's value."""
+    fv, ft, kw, desc, b = workload(args.workload, args.batch)
+    F, S = fv.shape[1], kw['image_size']
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_reference_arm(fv, ft, kw, steps=2, warmup=1)
+    line = {'impl': 'reference', 'metric': METRIC, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': max(3, args.warmup),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic'}
+    ref = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from ref_gpu import load_reference, reference_render
+            ref = load_reference()
+    except Exception as e:      # noqa: BLE001
+        line['reference_cuda_error'] = repr(e)[:200]
+    if ref is None:
+        if cpu is None:
+            cpu = cpu_reference_arm(fv, ft, kw, args.steps, args.warmup)
+        line.update({'value': cpu['value'], 'ms_per_step': cpu['ms_per_step'], 'gpu_launches': 0,
+                     'config': {'workload': desc, 'per_gpu_batch': b, 'timed_on': 'host CPU cores: the reference CUDA kernels compiled for the host '
+                                '(oracle/_ref) -- no GPU or no baseline/_ref build available'},
+                     'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                     'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
+        return line
+
+    import torch
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    B = b
+    gcol = torch.randn(B, 4, S, S, generator=torch.Generator().manual_seed(2))
+    d_fv, d_ft, d_g = fv.to(dev), ft.to(dev), gcol.to(dev)
+
+    def step():
+        a, t = d_fv.clone().requires_grad_(True), d_ft.clone().requires_grad_(True)
+        reference_render(ref, a, t, **kw).backward(d_g)
+        return a.grad, t.grad
+
+    warm = max(1, min(args.warmup, 2))          # one reference step is ~1.8 s at B = 64: keep the arm within minutes
+    steps = max(1, min(args.steps, 5))
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1) / steps
+    pairs = B * S * S * F
+    # end to end: pinned host buffers, copies inside the timed region
+    h_fv, h_ft, h_g = fv.pin_memory(), ft.pin_memory(), gcol.pin_memory()
+    h_img = torch.empty(B, 4, S, S).pin_memory()
+    h_gf, h_gt = torch.empty_like(fv).pin_memory(), torch.empty_like(ft).pin_memory()
+
+    def e2e_step():
+        a = h_fv.to(dev, non_blocking=True).requires_grad_(True)
+        t = h_ft.to(dev, non_blocking=True).requires_grad_(True)
+        g = h_g.to(dev, non_blocking=True)
+        img = reference_render(ref, a, t, **kw)
+        img.backward(g)
+        h_img.copy_(img.detach(), non_blocking=True); h_gf.copy_(a.grad, non_blocking=True); h_gt.copy_(t.grad, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_step()
+    n_e2e = max(1, min(steps, 3))
+    w0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    e2e_s = (time.perf_counter() - w0) / n_e2e
+    line.update({'value': pairs / (ms * 1e-3) / 1e6, 'ms_per_step': ms, 'steps': steps, 'warmup': warm,
+                 'config': {'workload': desc, 'per_gpu_batch': B, 'global_batch': B, 'faces': F, 'image_size': S,
+                            'timed_on': "one B200: the reference's own CUDA kernels (unmodified sources, sm_100a build under baseline/_ref) through "
+                                        'gendr.functional.render + backward; the reference has no multi-GPU path, so the arm is always 1 GPU',
+                            'steps_note': 'steps/warmup clamped (one reference step takes seconds)'},
+                 'e2e': {'value': pairs / e2e_s / 1e6, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
+                         'h2d_bytes_per_step': int((h_fv.numel() + h_ft.numel() + h_g.numel()) * 4),
+                         'd2h_bytes_per_step': int((h_img.numel() + h_gf.numel() + h_gt.numel()) * 4)},
+                 'gpu_launches': 0, 'clocks': clocks})
+    if cpu is not None:
+        line['cpu_baseline'] = {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    return line
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', 0))
@@ -142,15 +238,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        fv, ft, kw, desc, b = workload(args.workload, args.batch)
-        r = cpu_reference_arm(fv, ft, kw, args.steps, args.warmup)
-        line = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': desc, 'per_gpu_batch': b, 'timed_on': 'host CPU cores (GenDR ships no CPU rasterizer: '
-                'its CUDA kernels compiled for the host through oracle/ref_shim.h)' if r['kind'] == 'reference' else 'host CPU cores (C port of the reference algorithm)'},
-                'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-                'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(args)))
         return
 
     import numpy as np
