@@ -1,0 +1,188 @@
+// scene_kernels.cuh -- the O(B*V) / O(B*F) steps on either side of the rasterizer, as CUDA kernels:
+//
+//   camera transform    look_at / look  +  perspective / orthogonal
+//                       (/root/reference/gendr/functional/look_at.py:11-68, look.py:11-56, gendr/transform.py:14-44,109-168)
+//   lighting            ambient + one directional light folded into surface textures
+//                       (/root/reference/gendr/lighting.py:37-71, gendr/functional/lighting.py:12-48,
+//                        surface normals gendr/mesh.py:104-108)
+//   and their backward passes (the reference gets those from autograd over ~30 small torch kernels).
+//
+// Layout: one thread per (batch item, vertex) for the camera, one thread per (batch item, face) for the lighting.  The
+// camera basis is recomputed per thread from the eye (about 40 flops) instead of being staged through memory by a
+// separate launch: these kernels are launch-latency bound, not bandwidth bound.
+//
+// Arithmetic: plain fp32, same formulas and the same clamps (F.normalize eps 1e-5 / 1e-6, relu) as the reference.  The
+// reference evaluates them with torch reductions and a cuBLAS batched matmul whose summation order is not specified, so
+// parity here is "a few ulp" (tests: rtol 2e-6 on screen-space vertices and lit textures), not bit-exact.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gendr {
+
+struct CameraParams {
+    int   mode;            // 0 = look_at (z axis = at - eye), 1 = look (z axis = direction)
+    int   perspective;     // 1 = perspective(viewing_angle), 0 = orthogonal(viewing_scale)
+    int   eye_stride;      // 3 = eyes [B,3], 0 = one eye shared by the batch
+    float at_or_dir[3];    // look_at: the point looked at; look: the viewing direction
+    float up[3];
+    float inv_width;       // 1 / tan(viewing_angle)   (transform.py:22-27 divides by z, then by width)
+    float width;           // tanf(viewing_angle in radians), fp32 like the reference
+    float scale;           // orthogonal scale
+};
+
+struct LightParams {
+    float ambient[3];      // intensity_ambient * color_ambient
+    float directional[3];  // intensity_directionals * color_directionals
+    float direction[3];
+};
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 scale3(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+// F.normalize(v, eps): v / max(||v||_2, eps)
+__device__ __forceinline__ f3 normalize3(f3 a, float eps, float* norm_out = nullptr) {
+    const float n = sqrtf(dot3(a, a));
+    if (norm_out) *norm_out = n;
+    const float d = fmaxf(n, eps);
+    return mk3(a.x / d, a.y / d, a.z / d);
+}
+__device__ __forceinline__ f3 load3(const float* p) { return mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+
+struct CameraBasis { f3 x, y, z, eye; };
+__device__ __forceinline__ CameraBasis camera_basis(const CameraParams& C, const float* __restrict__ eyes, int b) {
+    CameraBasis K;
+    K.eye = load3(eyes + (size_t)b * C.eye_stride);
+    const f3 t = mk3(C.at_or_dir[0], C.at_or_dir[1], C.at_or_dir[2]);
+    const f3 up = mk3(C.up[0], C.up[1], C.up[2]);
+    K.z = normalize3(C.mode == 0 ? sub3(t, K.eye) : t, 1e-5f);       // look_at.py:54 / look.py:43
+    K.x = normalize3(cross3(up, K.z), 1e-5f);                        // look_at.py:55
+    K.y = normalize3(cross3(K.z, K.x), 1e-5f);                       // look_at.py:56
+    return K;
+}
+
+// ---- forward: world -> screen space, one thread per vertex -----------------------------------------------------
+__global__ void __launch_bounds__(256) camera_forward_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ vertices,
+                                                             const float* __restrict__ eyes, float* __restrict__ screen, int B, int V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * V) return;
+    const int b = (int)(i / V);
+    const CameraBasis K = camera_basis(C, eyes, b);
+    const f3 d = sub3(load3(vertices + i * 3), K.eye);               // look_at.py:64 (only_rotate = False)
+    const float xc = dot3(d, K.x), yc = dot3(d, K.y), zc = dot3(d, K.z);   // look_at.py:66: matmul(v, r^T)
+    float xs, ys;
+    if (C.perspective) { xs = xc / zc / C.width; ys = yc / zc / C.width; }  // transform.py:25-27
+    else { xs = xc * C.scale; ys = yc * C.scale; }                          // transform.py:41-42
+    screen[i * 3 + 0] = xs; screen[i * 3 + 1] = ys; screen[i * 3 + 2] = zc;
+}
+
+// ---- backward: grad_screen [B,V,3] -> grad_vertices [B,V,3] (plain store: every thread owns its vertex) --------
+__global__ void __launch_bounds__(256) camera_backward_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ vertices,
+                                                              const float* __restrict__ eyes, const float* __restrict__ grad_screen,
+                                                              float* __restrict__ grad_vertices, int B, int V) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * V) return;
+    const int b = (int)(i / V);
+    const CameraBasis K = camera_basis(C, eyes, b);
+    const f3 g = load3(grad_screen + i * 3);
+    float gxc, gyc, gzc;
+    if (C.perspective) {
+        const f3 d = sub3(load3(vertices + i * 3), K.eye);
+        const float xc = dot3(d, K.x), yc = dot3(d, K.y), zc = dot3(d, K.z);
+        const float r = 1.f / (zc * C.width);                        // d(xs)/d(xc)
+        gxc = g.x * r; gyc = g.y * r;
+        gzc = g.z - (g.x * xc + g.y * yc) * r / zc;                  // xs = xc / zc / width  =>  d(xs)/d(zc) = -xs / zc
+    } else {
+        gxc = g.x * C.scale; gyc = g.y * C.scale; gzc = g.z;
+    }
+    // v_cam = R (v - eye)  =>  grad_v = R^T grad_cam
+    grad_vertices[i * 3 + 0] = gxc * K.x.x + gyc * K.y.x + gzc * K.z.x;
+    grad_vertices[i * 3 + 1] = gxc * K.x.y + gyc * K.y.y + gzc * K.z.y;
+    grad_vertices[i * 3 + 2] = gxc * K.x.z + gyc * K.y.z + gzc * K.z.z;
+}
+
+// ---- lighting of one face (surface textures) ---------------------------------------------------------------------
+// returns light[3]; n / norm / cosine are kept for the backward pass
+__device__ __forceinline__ void face_light(const LightParams& L, f3 v0, f3 v1, f3 v2, float light[3], f3* n_out = nullptr,
+                                           float* norm_out = nullptr, float* cos_out = nullptr) {
+    float norm;
+    const f3 n = normalize3(cross3(sub3(v2, v1), sub3(v0, v1)), 1e-6f, &norm);     // mesh.py:105-108
+    const float c = n.x * L.direction[0] + n.y * L.direction[1] + n.z * L.direction[2];
+    const float cosine = fmaxf(c, 0.f);                                            // functional/lighting.py:46 (relu)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) light[k] = L.ambient[k] + L.directional[k] * cosine;   // :22 and :47
+    if (n_out) *n_out = n;
+    if (norm_out) *norm_out = norm;
+    if (cos_out) *cos_out = c;
+}
+
+__device__ __forceinline__ int clamp_index(int vi, int V) { return min(max(vi, 0), V - 1); }
+
+// forward: lit_textures[b,f,t,:] = textures[b,f,t,:] * light(b,f)      (lighting.py:58)
+__global__ void __launch_bounds__(256) lighting_forward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ vertices,
+                                                               const int* __restrict__ face_index, long long index_batch_stride,
+                                                               const float* __restrict__ textures, float* __restrict__ lit, int B, int V,
+                                                               int F, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const long long b = i / F, f = i - b * F;
+    const int* idx = face_index + b * index_batch_stride + f * 3;
+    const float* vb = vertices + b * V * 3;
+    const f3 v0 = load3(vb + (size_t)clamp_index(__ldg(idx + 0), V) * 3), v1 = load3(vb + (size_t)clamp_index(__ldg(idx + 1), V) * 3),
+             v2 = load3(vb + (size_t)clamp_index(__ldg(idx + 2), V) * 3);
+    float light[3];
+    face_light(L, v0, v1, v2, light);
+    const float* src = textures + i * T * 3;
+    float* dst = lit + i * T * 3;
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dst[t * 3 + k] = __ldg(src + t * 3 + k) * light[k];
+}
+
+// backward: grad_lit [B,F,T,3] -> grad_textures [B,F,T,3] (store; may be null) and, through the surface normal, atomic
+// adds into grad_vertices [B,V,3] (which already holds the camera path's gradient; may be null).
+__global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ vertices,
+                                                                const int* __restrict__ face_index, long long index_batch_stride,
+                                                                const float* __restrict__ textures, const float* __restrict__ grad_lit,
+                                                                float* __restrict__ grad_textures, float* __restrict__ grad_vertices,
+                                                                int B, int V, int F, int T) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const long long b = i / F, f = i - b * F;
+    const int* idx = face_index + b * index_batch_stride + f * 3;
+    const int i0 = clamp_index(__ldg(idx + 0), V), i1 = clamp_index(__ldg(idx + 1), V), i2 = clamp_index(__ldg(idx + 2), V);
+    const float* vb = vertices + b * V * 3;
+    const f3 v0 = load3(vb + (size_t)i0 * 3), v1 = load3(vb + (size_t)i1 * 3), v2 = load3(vb + (size_t)i2 * 3);
+    float light[3], norm, c;
+    f3 n;
+    face_light(L, v0, v1, v2, light, &n, &norm, &c);
+    float G[3] = {0.f, 0.f, 0.f};                                    // d loss / d light
+    const float* tex = textures + i * T * 3;
+    const float* gl = grad_lit + i * T * 3;
+    for (int t = 0; t < T; ++t)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float g = __ldg(gl + t * 3 + k);
+            G[k] = fmaf(g, __ldg(tex + t * 3 + k), G[k]);
+            if (grad_textures) grad_textures[i * T * 3 + t * 3 + k] = g * light[k];
+        }
+    if (!grad_vertices || !(c > 0.f)) return;                        // relu: no gradient at or below 0
+    const float gcos = L.directional[0] * G[0] + L.directional[1] * G[1] + L.directional[2] * G[2];
+    if (gcos == 0.f) return;
+    const f3 gn = mk3(gcos * L.direction[0], gcos * L.direction[1], gcos * L.direction[2]);
+    f3 gc;                                                            // gradient w.r.t. the un-normalised cross product
+    if (norm > 1e-6f) gc = scale3(sub3(gn, scale3(n, dot3(n, gn))), 1.f / norm);
+    else gc = scale3(gn, 1e6f);                                       // clamped norm: n = c / eps
+    const f3 a = sub3(v2, v1), e = sub3(v0, v1);                      // c = a x e
+    const f3 ga = cross3(e, gc), ge = cross3(gc, a);
+    float* gv = grad_vertices + b * V * 3;
+    atomicAdd(gv + (size_t)i2 * 3 + 0, ga.x); atomicAdd(gv + (size_t)i2 * 3 + 1, ga.y); atomicAdd(gv + (size_t)i2 * 3 + 2, ga.z);
+    atomicAdd(gv + (size_t)i0 * 3 + 0, ge.x); atomicAdd(gv + (size_t)i0 * 3 + 1, ge.y); atomicAdd(gv + (size_t)i0 * 3 + 2, ge.z);
+    atomicAdd(gv + (size_t)i1 * 3 + 0, -(ga.x + ge.x)); atomicAdd(gv + (size_t)i1 * 3 + 1, -(ga.y + ge.y));
+    atomicAdd(gv + (size_t)i1 * 3 + 2, -(ga.z + ge.z));
+}
+
+}  // namespace gendr
