@@ -24,15 +24,37 @@ class RenderParams(C.Structure):
     ]
 
 
+class CameraParams(C.Structure):
+    """Mirror of `struct gendr_camera_params` (include/gendr_b200.h)."""
+    _fields_ = [('mode', C.c_int), ('perspective', C.c_int), ('viewing_angle', C.c_float), ('viewing_scale', C.c_float),
+                ('at_or_direction', C.c_float * 3), ('up', C.c_float * 3)]
+
+
+class LightParams(C.Structure):
+    """Mirror of `struct gendr_light_params` (include/gendr_b200.h)."""
+    _fields_ = [('intensity_ambient', C.c_float), ('color_ambient', C.c_float * 3),
+                ('intensity_directional', C.c_float), ('color_directional', C.c_float * 3), ('direction', C.c_float * 3)]
+
+
 # every symbol include/gendr_b200.h declares: (restype, argtypes)
 _P, _F, _I, _SZ = C.c_void_p, C.c_float, C.c_int, C.c_size_t
 _PP = C.POINTER(RenderParams)
+_PC, _PL = C.POINTER(CameraParams), C.POINTER(LightParams)
 SIGNATURES = {
     'gendr_workspace_bytes': (_SZ, [_I, _I]),
     'gendr_forward_render': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _P, _SZ, _P]),
     'gendr_backward_render': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _I, _P, _SZ, _P]),
-    'gendr_forward_render_indexed': (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
-    'gendr_backward_render_indexed': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _PP, _I, _P, _SZ, _P]),
+    'gendr_forward_render_indexed': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_backward_render_indexed': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _PP, _I, _P, _SZ, _P]),
+    'gendr_forward_render_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_backward_render_aa': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _I, _P, _SZ, _P]),
+    'gendr_camera_forward': (_I, [_P, _P, _I, _P, _I, _I, _PC, _P]),
+    'gendr_camera_backward': (_I, [_P, _P, _I, _P, _P, _I, _I, _PC, _P]),
+    'gendr_lighting_forward': (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _PL, _P]),
+    'gendr_lighting_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _PL, _P]),
+    'gendr_scene_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
+    'gendr_scene_forward': (_I, [_P, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_scene_backward': (_I, [_P, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
     'gendr_render_forward_backward_host': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _PP]),
     'gendr_sigmoid_forward': (_F, [_I, _F, _F, _F, _F, _F]),
     'gendr_sigmoid_backward': (_F, [_I, _F, _F, _F, _F, _F]),

@@ -3,6 +3,7 @@
 // (inst_dist.cu) and reports errors.  No torch, no CPU compute path: every entry point runs CUDA kernels.
 #include "../../include/gendr_b200.h"
 #include "render_kernels.cuh"
+#include "scene_kernels.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -441,8 +442,48 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     return 0;
 }
 
+static int check_aa(const RenderParams& P, const void* pooled_or_flag) {
+    if (pooled_or_flag && (P.S & 1)) return fail(GENDR_ERR_INVALID_ARGUMENT, "anti-aliasing needs an even (supersampled) image_size");
+    return 0;
+}
+
+static int forward_indexed_impl(const RenderParams& P, const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                float* aggrs_info, float* soft_colors, float* pooled_colors, int num_vertices, void* workspace, cudaStream_t st) {
+    const long long n = (long long)P.B * P.F;
+    if (n > 0) {
+        prep_indexed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, vertices, face_index, index_shared ? 0 : (long long)P.F * 3, num_vertices,
+                                                                       ws_records(workspace), ws_rects(workspace, P.B, P.F));
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "prep_indexed_kernel launch");
+    }
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, P.B, P.F);
+    io.textures = textures; io.tex_elems = (long long)P.B * P.F * P.T * 3;
+    io.soft_colors = soft_colors; io.aggrs = aggrs_info; io.pooled = pooled_colors;
+    return run_render(P, io, false, st);
+}
+
+static int backward_indexed_impl(const RenderParams& P, const int* face_index, int index_shared, const float* textures, const float* soft_colors,
+                                 const float* aggrs_info, float* grad_vertices, float* grad_textures, const float* grad_soft_colors,
+                                 int grad_is_pooled, int num_vertices, int zero_grads, void* workspace, cudaStream_t st) {
+    if (zero_grads) {
+        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)P.B * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
+        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)P.B * P.F * P.T * 3 * sizeof(float), st), "zero grad_textures");
+    }
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, P.B, P.F);    // left there by the indexed forward
+    io.textures = textures; io.tex_elems = (long long)P.B * P.F * P.T * 3;
+    io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
+    io.grad_colors = grad_soft_colors; io.grad_textures = grad_textures; io.grad_pooled = grad_is_pooled ? 1 : 0;
+    io.grad_vertices = grad_vertices; io.face_index = face_index; io.index_batch_stride = index_shared ? 0 : (long long)P.F * 3;
+    io.num_vertices = num_vertices;
+    return run_render(P, io, true, st);
+}
+
 int gendr_forward_render_indexed(const float* vertices, const int* face_index, int index_shared, const float* textures, float* aggrs_info,
-                                 float* soft_colors, int batch, int num_vertices, int num_faces, int texture_size,
+                                 float* soft_colors, float* pooled_colors, int batch, int num_vertices, int num_faces, int texture_size,
                                  const gendr_render_params* params, void* workspace, size_t workspace_bytes, void* stream) {
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_forward_render_indexed");
@@ -450,50 +491,272 @@ int gendr_forward_render_indexed(const float* vertices, const int* face_index, i
     if (((!vertices || !face_index || !textures) && num_faces > 0) || !aggrs_info || !soft_colors || !workspace || num_vertices < 1)
         return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render_indexed");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    if (int e = check_aa(P, pooled_colors)) return e;
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const long long n = (long long)batch * num_faces;
-    if (n > 0) {
-        prep_indexed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, vertices, face_index, index_shared ? 0 : (long long)num_faces * 3, num_vertices,
-                                                                       ws_records(workspace), ws_rects(workspace, batch, num_faces));
-        g_launches++;
-        GENDR_CUDA(cudaGetLastError(), "prep_indexed_kernel launch");
-    }
-    KernelIO io;
-    memset(&io, 0, sizeof io);
-    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
-    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
-    io.soft_colors = soft_colors; io.aggrs = aggrs_info;
-    return run_render(P, io, false, st);
+    return forward_indexed_impl(P, vertices, face_index, index_shared, textures, aggrs_info, soft_colors, pooled_colors, num_vertices, workspace,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gendr_backward_render_indexed(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
                                   const float* aggrs_info, float* grad_vertices, float* grad_textures, const float* grad_soft_colors,
-                                  int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
-                                  int zero_grads, void* workspace, size_t workspace_bytes, void* stream) {
+                                  int grad_is_pooled, int batch, int num_vertices, int num_faces, int texture_size,
+                                  const gendr_render_params* params, int zero_grads, void* workspace, size_t workspace_bytes, void* stream) {
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_indexed");
     if (batch == 0) return 0;
     if (!face_index || !textures || !soft_colors || !aggrs_info || !grad_vertices || !grad_soft_colors || !workspace || num_vertices < 1)
         return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    if (int e = check_aa(P, grad_is_pooled ? grad_soft_colors : nullptr)) return e;
     DeviceScope dev;
     GENDR_CUDA(dev.enter(grad_vertices), "selecting the device that owns `grad_vertices`");
+    return backward_indexed_impl(P, face_index, index_shared, textures, soft_colors, aggrs_info, grad_vertices, grad_textures, grad_soft_colors,
+                                 grad_is_pooled, num_vertices, zero_grads, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- fused 2x anti-aliasing on the face-vertex path ----------------------------------------
+int gendr_forward_render_aa(const float* faces, const float* textures, float* aggrs_info, float* soft_colors, float* pooled_colors, int batch,
+                            int num_faces, int texture_size, const gendr_render_params* params, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_forward_render_aa");
+    if (batch == 0) return 0;
+    if (((!faces || !textures) && num_faces > 0) || !aggrs_info || !soft_colors || !pooled_colors || !workspace)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_forward_render_aa");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    if (int e = check_aa(P, pooled_colors)) return e;
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
+    KernelIO io;
+    memset(&io, 0, sizeof io);
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
+    io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
+    io.soft_colors = soft_colors; io.aggrs = aggrs_info; io.pooled = pooled_colors;
+    return run_render(P, io, false, st);
+}
+
+int gendr_backward_render_aa(const float* faces, const float* textures, const float* soft_colors, const float* aggrs_info, float* grad_faces,
+                             float* grad_textures, const float* grad_pooled_colors, int batch, int num_faces, int texture_size,
+                             const gendr_render_params* params, int workspace_valid, int zero_grads, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_aa");
+    if (batch == 0) return 0;
+    if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_pooled_colors || !workspace)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_aa");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    if (int e = check_aa(P, grad_pooled_colors)) return e;
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!workspace_valid) if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
     if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)batch * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
+        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
         if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
     }
     KernelIO io;
     memset(&io, 0, sizeof io);
-    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);    // left there by the indexed forward
+    io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
     io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
-    io.grad_colors = grad_soft_colors; io.grad_textures = grad_textures;
-    io.grad_vertices = grad_vertices; io.face_index = face_index; io.index_batch_stride = index_shared ? 0 : (long long)num_faces * 3;
-    io.num_vertices = num_vertices;
+    io.grad_colors = grad_pooled_colors; io.grad_pooled = 1; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
     return run_render(P, io, true, st);
+}
+
+// ---- camera transform + lighting ----------------------------------------------------------
+static int make_camera(CameraParams& C, const gendr_camera_params* u, int eyes_batched) {
+    if (!u || (u->mode != 0 && u->mode != 1)) return GENDR_ERR_INVALID_ARGUMENT;
+    memset(&C, 0, sizeof C);
+    C.mode = u->mode; C.perspective = u->perspective ? 1 : 0; C.eye_stride = eyes_batched ? 3 : 0;
+    for (int k = 0; k < 3; ++k) { C.at_or_dir[k] = u->at_or_direction[k]; C.up[k] = u->up[k]; }
+    // transform.py:20-22: torch.tan(torch.tensor(angle / 180 * math.pi, dtype=torch.float32))
+    C.width = tanf((float)((double)u->viewing_angle / 180. * 3.14159265358979323846));
+    C.inv_width = 1.f / C.width;
+    C.scale = u->viewing_scale;
+    return 0;
+}
+static void make_light(LightParams& L, const gendr_light_params* u) {
+    for (int k = 0; k < 3; ++k) {
+        L.ambient[k] = u->intensity_ambient * u->color_ambient[k];
+        L.directional[k] = u->intensity_directional * u->color_directional[k];
+        L.direction[k] = u->direction[k];
+    }
+}
+static unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
+
+static int camera_forward_impl(const CameraParams& C, const float* vertices, const float* eyes, float* screen, int B, int V, cudaStream_t st) {
+    const long long n = (long long)B * V;
+    if (n == 0) return 0;
+    camera_forward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, eyes, screen, B, V);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "camera_forward_kernel launch");
+    return 0;
+}
+static int camera_backward_impl(const CameraParams& C, const float* vertices, const float* eyes, const float* grad_screen, float* grad_vertices,
+                                int B, int V, cudaStream_t st) {
+    const long long n = (long long)B * V;
+    if (n == 0) return 0;
+    camera_backward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, eyes, grad_screen, grad_vertices, B, V);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "camera_backward_kernel launch");
+    return 0;
+}
+static int lighting_forward_impl(const LightParams& L, const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                 float* lit, int B, int V, int F, int T, cudaStream_t st) {
+    const long long n = (long long)B * F;
+    if (n == 0) return 0;
+    lighting_forward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, face_index, index_shared ? 0 : (long long)F * 3, textures, lit, B, V, F, T);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "lighting_forward_kernel launch");
+    return 0;
+}
+static int lighting_backward_impl(const LightParams& L, const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                  const float* grad_lit, float* grad_textures, float* grad_vertices, int B, int V, int F, int T, cudaStream_t st) {
+    const long long n = (long long)B * F;
+    if (n == 0) return 0;
+    lighting_backward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, face_index, index_shared ? 0 : (long long)F * 3, textures, grad_lit,
+                                                            grad_textures, grad_vertices, B, V, F, T);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "lighting_backward_kernel launch");
+    return 0;
+}
+
+int gendr_camera_forward(const float* vertices, const float* eyes, int eyes_batched, float* screen_vertices, int batch, int num_vertices,
+                         const gendr_camera_params* camera, void* stream) {
+    CameraParams C;
+    if (make_camera(C, camera, eyes_batched) || batch < 0 || num_vertices < 0) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_camera_forward");
+    if (batch == 0 || num_vertices == 0) return 0;
+    if (!vertices || !eyes || !screen_vertices) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_forward");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    return camera_forward_impl(C, vertices, eyes, screen_vertices, batch, num_vertices, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_batched, const float* grad_screen_vertices, float* grad_vertices,
+                          int batch, int num_vertices, const gendr_camera_params* camera, void* stream) {
+    CameraParams C;
+    if (make_camera(C, camera, eyes_batched) || batch < 0 || num_vertices < 0) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_camera_backward");
+    if (batch == 0 || num_vertices == 0) return 0;
+    if (!vertices || !eyes || !grad_screen_vertices || !grad_vertices) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_backward");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    return camera_backward_impl(C, vertices, eyes, grad_screen_vertices, grad_vertices, batch, num_vertices, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int gendr_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, float* lit_textures, int batch,
+                           int num_vertices, int num_faces, int texture_size, const gendr_light_params* light, void* stream) {
+    if (!light || batch < 0 || num_faces < 0 || num_vertices < 1 || texture_size < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_lighting_forward");
+    if (batch == 0 || num_faces == 0) return 0;
+    if (!vertices || !face_index || !textures || !lit_textures) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_lighting_forward");
+    LightParams L;
+    make_light(L, light);
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    return lighting_forward_impl(L, vertices, face_index, index_shared, textures, lit_textures, batch, num_vertices, num_faces, texture_size,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int gendr_lighting_backward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* grad_lit_textures,
+                            float* grad_textures, float* grad_vertices, int batch, int num_vertices, int num_faces, int texture_size,
+                            const gendr_light_params* light, void* stream) {
+    if (!light || batch < 0 || num_faces < 0 || num_vertices < 1 || texture_size < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_lighting_backward");
+    if (batch == 0 || num_faces == 0) return 0;
+    if (!vertices || !face_index || !textures || !grad_lit_textures) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_lighting_backward");
+    LightParams L;
+    make_light(L, light);
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    return lighting_backward_impl(L, vertices, face_index, index_shared, textures, grad_lit_textures, grad_textures, grad_vertices, batch,
+                                  num_vertices, num_faces, texture_size, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// scene workspace: [render workspace | screen vertices B*V*3 | grad screen vertices B*V*3 | lit textures B*F*T*3 | grad lit B*F*T*3]
+struct SceneWs { void* render; float* screen; float* grad_screen; float* lit; float* grad_lit; };
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static SceneWs scene_ws(void* ws, int B, int V, int F, int T) {
+    SceneWs w;
+    char* p = reinterpret_cast<char*>(ws);
+    w.render = p; p += al256(gendr_workspace_bytes(B, F));
+    w.screen = reinterpret_cast<float*>(p); p += al256((size_t)B * V * 12);
+    w.grad_screen = reinterpret_cast<float*>(p); p += al256((size_t)B * V * 12);
+    w.lit = reinterpret_cast<float*>(p); p += al256((size_t)B * F * T * 12);
+    w.grad_lit = reinterpret_cast<float*>(p);
+    return w;
+}
+size_t gendr_scene_workspace_bytes(int batch, int num_vertices, int num_faces, int texture_size) {
+    if (batch < 0 || num_vertices < 0 || num_faces < 0 || texture_size < 1) return 0;
+    return al256(gendr_workspace_bytes(batch, num_faces)) + 2 * al256((size_t)batch * num_vertices * 12) +
+           2 * al256((size_t)batch * num_faces * texture_size * 12) + 256;
+}
+
+int gendr_scene_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
+                        const gendr_camera_params* camera, const gendr_light_params* light, float* aggrs_info, float* soft_colors,
+                        float* pooled_colors, int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    CameraParams C;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_scene_forward");
+    if (make_camera(C, camera, eyes_batched) || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid camera passed to gendr_scene_forward");
+    if (P.texture_type != 0) return fail(GENDR_ERR_INVALID_ARGUMENT, "gendr_scene_forward supports surface textures only");
+    if (batch == 0) return 0;
+    if (!vertices || !eyes || ((!face_index || !textures) && num_faces > 0) || !aggrs_info || !soft_colors || !workspace)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_scene_forward");
+    if (workspace_bytes < gendr_scene_workspace_bytes(batch, num_vertices, num_faces, texture_size))
+        return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_scene_workspace_bytes)");
+    if (int e = check_aa(P, pooled_colors)) return e;
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const SceneWs w = scene_ws(workspace, batch, num_vertices, num_faces, texture_size);
+    if (int e = camera_forward_impl(C, vertices, eyes, w.screen, batch, num_vertices, st)) return e;
+    const float* tex = textures;
+    if (light) {
+        LightParams L;
+        make_light(L, light);
+        if (int e = lighting_forward_impl(L, vertices, face_index, index_shared, textures, w.lit, batch, num_vertices, num_faces, texture_size, st)) return e;
+        tex = w.lit;
+    }
+    return forward_indexed_impl(P, w.screen, face_index, index_shared, tex, aggrs_info, soft_colors, pooled_colors, num_vertices, w.render, st);
+}
+
+int gendr_scene_backward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
+                         const gendr_camera_params* camera, const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
+                         const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures, int batch,
+                         int num_vertices, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    CameraParams C;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_scene_backward");
+    if (make_camera(C, camera, eyes_batched) || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid camera passed to gendr_scene_backward");
+    if (P.texture_type != 0) return fail(GENDR_ERR_INVALID_ARGUMENT, "gendr_scene_backward supports surface textures only");
+    if (batch == 0) return 0;
+    if (!vertices || !eyes || !face_index || !textures || !soft_colors || !aggrs_info || !grad_soft_colors || !grad_vertices || !workspace)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_scene_backward");
+    if (workspace_bytes < gendr_scene_workspace_bytes(batch, num_vertices, num_faces, texture_size))
+        return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_scene_workspace_bytes)");
+    if (int e = check_aa(P, grad_is_pooled ? grad_soft_colors : nullptr)) return e;
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const SceneWs w = scene_ws(workspace, batch, num_vertices, num_faces, texture_size);
+    // the rasterizer's texture gradient: w.r.t. the LIT textures when lighting is on (always needed then: it also feeds the
+    // normals' gradient), else straight into the caller's grad_textures
+    float* g_tex = light ? w.grad_lit : grad_textures;
+    GENDR_CUDA(cudaMemsetAsync(w.grad_screen, 0, (size_t)batch * num_vertices * 12, st), "zero screen-space vertex gradient");
+    if (g_tex) GENDR_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)batch * num_faces * texture_size * 12, st), "zero texture gradient");
+    if (int e = backward_indexed_impl(P, face_index, index_shared, light ? w.lit : textures, soft_colors, aggrs_info, w.grad_screen, g_tex,
+                                      grad_soft_colors, grad_is_pooled, num_vertices, 0, w.render, st)) return e;
+    if (int e = camera_backward_impl(C, vertices, eyes, w.grad_screen, grad_vertices, batch, num_vertices, st)) return e;
+    if (light) {
+        LightParams L;
+        make_light(L, light);
+        if (int e = lighting_backward_impl(L, vertices, face_index, index_shared, textures, w.grad_lit, grad_textures, grad_vertices, batch,
+                                           num_vertices, num_faces, texture_size, st)) return e;
+    }
+    return 0;
 }
 
 float gendr_sigmoid_forward(int id, float sign, float x, float scale, float shape, float shift) {

@@ -81,6 +81,25 @@ def backward_render_raw(faces, textures, soft_colors, aggrs_info, grad_faces, gr
         int(workspace_valid), int(zero_grads), workspace.data_ptr(), workspace.numel(), _stream(faces.device)))
 
 
+def forward_render_aa_raw(faces, textures, aggrs_info, soft_colors, pooled_colors, params, workspace):
+    lib = _lib.load()
+    B, F = int(faces.shape[0]), int(faces.shape[1])
+    _lib.check(lib.gendr_forward_render_aa(
+        faces.data_ptr(), textures.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(), pooled_colors.data_ptr(), B, F,
+        int(textures.shape[2]), params, workspace.data_ptr(), workspace.numel(), _stream(faces.device)))
+
+
+def backward_render_aa_raw(faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures, grad_pooled_colors, params,
+                           workspace, workspace_valid, zero_grads):
+    lib = _lib.load()
+    B, F = int(faces.shape[0]), int(faces.shape[1])
+    _lib.check(lib.gendr_backward_render_aa(
+        faces.data_ptr(), textures.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_faces.data_ptr(),
+        grad_textures.data_ptr() if grad_textures is not None else None, grad_pooled_colors.data_ptr(), B, F,
+        int(textures.shape[2]), params, int(workspace_valid), int(zero_grads), workspace.data_ptr(), workspace.numel(),
+        _stream(faces.device)))
+
+
 def forward_render(faces, textures, faces_info, aggrs_info, soft_colors, image_size, dist_func, dist_scale,
                    dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
                    aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type):

@@ -39,7 +39,7 @@ class GenDRFunction(Function):
                 dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None,
                 dist_eps=1e4, aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
                 aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3, near=1, far=100,
-                double_side=True, texture_type='surface'):
+                double_side=True, texture_type='surface', anti_aliasing=False):
         assert dist_scale >= 0, dist_scale      # functional/renderer.py:96
         assert dist_eps >= 1, dist_eps          # functional/renderer.py:101
         if not face_vertices.is_cuda:
@@ -59,11 +59,17 @@ class GenDRFunction(Function):
         soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=faces.device)
         aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=faces.device)
         workspace = _ext.workspace_for(faces)
+        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=faces.device) if anti_aliasing else None
         with torch.cuda.device(faces.device):
-            _ext.forward_render_raw(faces, tex, None, aggrs_info, soft_colors, params, False, workspace)
-        ctx.params = params
+            if anti_aliasing:      # fused F.avg_pool2d(images, 2, 2) (gendr/renderer.py:92-93)
+                _ext.forward_render_aa_raw(faces, tex, aggrs_info, soft_colors, pooled, params, workspace)
+            else:
+                _ext.forward_render_raw(faces, tex, None, aggrs_info, soft_colors, params, False, workspace)
+        ctx.params, ctx.anti_aliasing = params, bool(anti_aliasing)
         ctx.shapes = (face_vertices.shape, textures.shape)
         ctx.save_for_backward(faces, tex, soft_colors, aggrs_info, workspace)
+        if anti_aliasing:
+            return pooled
         return soft_colors
 
     @staticmethod
@@ -74,10 +80,14 @@ class GenDRFunction(Function):
         grad_faces = torch.empty_like(faces)
         grad_tex = torch.empty_like(tex) if want_tex else None
         with torch.cuda.device(faces.device):
-            _ext.backward_render_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
-                                     ctx.params, workspace, True, True)
+            if ctx.anti_aliasing:
+                _ext.backward_render_aa_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
+                                            ctx.params, workspace, True, True)
+            else:
+                _ext.backward_render_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
+                                         ctx.params, workspace, True, True)
         fshape, tshape = ctx.shapes
-        return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 17
+        return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 18
 
 
 class GenDRIndexedFunction(Function):
@@ -88,7 +98,7 @@ class GenDRIndexedFunction(Function):
     @staticmethod
     def forward(ctx, vertices, faces, textures, image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape,
                 dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma,
-                near, far, double_side, texture_type):
+                near, far, double_side, texture_type, anti_aliasing=False):
         assert dist_scale >= 0, dist_scale
         assert dist_eps >= 1, dist_eps
         if not vertices.is_cuda:
@@ -110,14 +120,16 @@ class GenDRIndexedFunction(Function):
         aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=verts.device)
         lib = _ext._lib.load()
         workspace = torch.empty(lib.gendr_workspace_bytes(B, F), dtype=torch.uint8, device=verts.device)
+        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=verts.device) if anti_aliasing else None
         with torch.cuda.device(verts.device):
             _ext._lib.check(lib.gendr_forward_render_indexed(
                 verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
-                B, V, F, int(tex.shape[2]), params, workspace.data_ptr(), workspace.numel(),
-                torch.cuda.current_stream(verts.device).cuda_stream))
+                pooled.data_ptr() if anti_aliasing else None, B, V, F, int(tex.shape[2]), params, workspace.data_ptr(),
+                workspace.numel(), torch.cuda.current_stream(verts.device).cuda_stream))
         ctx.params, ctx.dims, ctx.shapes = params, (B, V, F, int(tex.shape[2]), shared), (vertices.shape, textures.shape)
+        ctx.anti_aliasing = bool(anti_aliasing)
         ctx.save_for_backward(index, tex, soft_colors, aggrs_info, workspace)
-        return soft_colors
+        return pooled if anti_aliasing else soft_colors
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
@@ -131,30 +143,140 @@ class GenDRIndexedFunction(Function):
         with torch.cuda.device(tex.device):
             _ext._lib.check(lib.gendr_backward_render_indexed(
                 index.data_ptr(), int(shared), tex.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
-                grad_vertices.data_ptr(), grad_tex.data_ptr() if want_tex else None, grad_soft_colors.data_ptr(), B, V, F, T,
-                ctx.params, 1, workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(tex.device).cuda_stream))
+                grad_vertices.data_ptr(), grad_tex.data_ptr() if want_tex else None, grad_soft_colors.data_ptr(),
+                int(ctx.anti_aliasing), B, V, F, T, ctx.params, 1, workspace.data_ptr(), workspace.numel(),
+                torch.cuda.current_stream(tex.device).cuda_stream))
         vshape, tshape = ctx.shapes
-        return (grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None) + (None,) * 17
+        return (grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None) + (None,) * 18
 
 
 def render_indexed(vertices, faces, textures, image_size=256, background_color=[0, 0, 0],
                    dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
                    aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
                    aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
-                   near=1, far=100, double_side=True, texture_type='surface'):
+                   near=1, far=100, double_side=True, texture_type='surface', anti_aliasing=False):
     """Same as render(), for (vertices [B,V,3], faces [B,F,3] | [F,3]) instead of face_vertices [B,F,3,3]."""
     return GenDRIndexedFunction.apply(vertices, faces, textures, image_size, background_color, dist_func, dist_scale,
                                       dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
-                                      aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type)
+                                      aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type,
+                                      anti_aliasing)
 
 
 def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
            dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
            aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
            aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
-           near=1, far=100, double_side=True, texture_type='surface'):
+           near=1, far=100, double_side=True, texture_type='surface', anti_aliasing=False):
     """face_vertices [B,F,3,3] (screen space), textures [B,F,T,3] -> RGBA images [B,4,S,S].
-    Keyword surface and defaults of gendr.functional.render (functional/renderer.py:239-262)."""
+    Keyword surface and defaults of gendr.functional.render (functional/renderer.py:239-262).  One addition:
+    anti_aliasing=True treats image_size as the supersampled side and returns the 2x2-averaged image
+    [B,4,S/2,S/2] -- F.avg_pool2d(render(...), 2, 2) of gendr/renderer.py:92-93, fused into the kernels (bit-identical)."""
     return GenDRFunction.apply(face_vertices, textures, image_size, background_color, dist_func, dist_scale,
                                dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
-                               aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type)
+                               aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type,
+                               anti_aliasing)
+
+
+def make_camera_params(mode='look_at', perspective=True, viewing_angle=30., viewing_scale=1.0, at=(0, 0, 0), up=(0, 1, 0),
+                       direction=(0, 0, 1)):
+    c = _ext._lib.CameraParams()
+    c.mode = {'look_at': 0, 'look': 1}[mode]
+    c.perspective = int(bool(perspective))
+    c.viewing_angle, c.viewing_scale = float(viewing_angle), float(viewing_scale)
+    target = at if c.mode == 0 else direction
+    for k in range(3):
+        c.at_or_direction[k] = float(target[k])
+        c.up[k] = float(up[k])
+    return c
+
+
+def make_light_params(intensity_ambient=0.5, color_ambient=(1, 1, 1), intensity_directional=0.5,
+                      color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    p = _ext._lib.LightParams()
+    p.intensity_ambient, p.intensity_directional = float(intensity_ambient), float(intensity_directional)
+    for k in range(3):
+        p.color_ambient[k] = float(color_ambient[k])
+        p.color_directional[k] = float(color_directional[k])
+        p.direction[k] = float(direction[k])
+    return p
+
+
+class GenDRSceneFunction(Function):
+    """Lighting -> LookAt/Look -> GenDR for a world-space mesh in ONE autograd node:
+    the camera transform (gendr/functional/look_at.py:11-68, transform.py:14-44), the surface lighting
+    (gendr/lighting.py:48-58), the vertices[faces] gather and the rasterizer run as four launches forward and three
+    backward (gendr_scene_forward / gendr_scene_backward); gradients w.r.t. the world-space vertices (camera path +
+    normals' path) and the unlit textures."""
+    @staticmethod
+    def forward(ctx, vertices, faces, textures, eyes, camera, light, params, anti_aliasing):
+        if not vertices.is_cuda:
+            raise TypeError('GenDR only supports CUDA Tensors.')
+        verts = vertices.detach().to(torch.float32).contiguous()
+        dev = verts.device
+        B, V = verts.shape[:2]
+        index = faces.detach().to(device=dev, dtype=torch.int32).contiguous()
+        shared = index.ndimension() == 2
+        F = index.shape[-2]
+        tex = textures.detach().to(device=dev, dtype=torch.float32).contiguous()
+        tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
+        T = int(tex.shape[2])
+        eyes = eyes.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eyes_batched = eyes.ndimension() == 2
+        if eyes_batched and eyes.shape[0] != B:
+            raise ValueError('eyes must be [3] or [batch, 3]')
+        S = int(params.image_size)
+        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=dev)
+        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=dev)
+        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=dev) if anti_aliasing else None
+        lib = _ext._lib.load()
+        workspace = torch.empty(lib.gendr_scene_workspace_bytes(B, V, F, T), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _ext._lib.check(lib.gendr_scene_forward(
+                verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
+                aggrs_info.data_ptr(), soft_colors.data_ptr(), pooled.data_ptr() if anti_aliasing else None, B, V, F, T, params,
+                workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(dev).cuda_stream))
+        ctx.cfg = (camera, light, params, bool(anti_aliasing), (B, V, F, T, shared, eyes_batched), (vertices.shape, textures.shape))
+        ctx.save_for_backward(verts, index, tex, eyes, soft_colors, aggrs_info, workspace)
+        return pooled if anti_aliasing else soft_colors
+
+    @staticmethod
+    def backward(ctx, grad_images):
+        verts, index, tex, eyes, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+        camera, light, params, aa, (B, V, F, T, shared, eyes_batched), (vshape, tshape) = ctx.cfg
+        grad_images = grad_images.to(torch.float32).contiguous()
+        want_tex = ctx.needs_input_grad[2]
+        grad_vertices = torch.empty_like(verts)
+        grad_tex = torch.empty_like(tex) if want_tex else None
+        lib = _ext._lib.load()
+        with torch.cuda.device(verts.device):
+            _ext._lib.check(lib.gendr_scene_backward(
+                verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
+                soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_images.data_ptr(), int(aa), grad_vertices.data_ptr(),
+                grad_tex.data_ptr() if want_tex else None, B, V, F, T, params, workspace.data_ptr(), workspace.numel(),
+                torch.cuda.current_stream(verts.device).cuda_stream))
+        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, None, None, None, None, None
+
+
+def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, image_size=256, background_color=[0, 0, 0],
+                 dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None, dist_eps=1e4,
+                 aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
+                 aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
+                 near=1, far=100, double_side=True, texture_type='surface', anti_aliasing=False):
+    """World-space mesh (vertices [B,V,3], faces [B,F,3] | [F,3], surface textures [B,F,T,3]) seen from `eyes` ([B,3] | [3])
+    -> RGBA images: lighting(mesh); transform(mesh); renderer(mesh) of the reference's scripts in one fused node.
+    camera: dict for make_camera_params (mode, perspective, viewing_angle, viewing_scale, at, up, direction);
+    lighting: dict for make_light_params, or None for no lighting step."""
+    assert dist_scale >= 0, dist_scale
+    assert dist_eps >= 1, dist_eps
+    if texture_type != 'surface':
+        raise ValueError('render_scene supports surface textures only')
+    params = _ext.make_params(
+        image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
+        _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
+        _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
+        TEXTURE_TYPE_IDS[texture_type], background_color)
+    cam = make_camera_params(**(camera or {}))
+    light = make_light_params(**lighting) if lighting is not None else None
+    if not torch.is_tensor(eyes):
+        eyes = torch.tensor(eyes, dtype=torch.float32, device=vertices.device)
+    return GenDRSceneFunction.apply(vertices, faces, textures, eyes, cam, light, params, anti_aliasing)

@@ -2,8 +2,15 @@
 import torch
 import torch.nn as nn
 
+import copy
+
 from . import functional
+from . import mesh as _mesh
 from .mesh import Mesh
+
+
+def _is_vec3(v):
+    return isinstance(v, (list, tuple)) and len(v) == 3 and all(isinstance(x, (int, float)) for x in v)
 
 
 class AmbientLighting(nn.Module):
@@ -31,7 +38,8 @@ class Lighting(nn.Module):
         self.ambient = AmbientLighting(intensity_ambient, color_ambient)
         self.directionals = nn.ModuleList([DirectionalLighting(intensity_directionals, color_directionals, directions)])
 
-    def forward(self, mesh):
+    def lit_textures(self, mesh):
+        """textures * (ambient + directional light), the torch implementation (gendr/lighting.py:48-64)."""
         if mesh.texture_type == 'surface':
             like, normals, expand = mesh.faces, mesh.surface_normals, lambda l: l[:, :, None, :]
         elif mesh.texture_type == 'vertex':
@@ -41,4 +49,26 @@ class Lighting(nn.Module):
         light = self.ambient(torch.zeros(like.shape, dtype=torch.float32, device=mesh.device))
         for directional in self.directionals:
             light = directional(light, normals)
-        return Mesh(mesh.vertices, mesh.faces, mesh.textures * expand(light), mesh.texture_res, mesh.texture_type)
+        return mesh.textures * expand(light)
+
+    def fused_params(self):
+        """dict for functional.make_light_params, or None when this configuration has no fused kernel (tensor-valued
+        colours/directions, several directional lights)."""
+        if len(self.directionals) != 1:
+            return None
+        d, a = self.directionals[0], self.ambient
+        if not (_is_vec3(a.light_color) and _is_vec3(d.light_color) and _is_vec3(d.light_direction)):
+            return None
+        if not all(isinstance(x, (int, float)) for x in (a.light_intensity, d.light_intensity)):
+            return None
+        return dict(intensity_ambient=a.light_intensity, color_ambient=tuple(a.light_color),
+                    intensity_directional=d.light_intensity, color_directional=tuple(d.light_color),
+                    direction=tuple(d.light_direction))
+
+    def forward(self, mesh):
+        if (_mesh.FUSE_SCENE and mesh.texture_type == 'surface' and mesh._pending_light is None and mesh._pending_camera is None
+                and mesh._vertices.is_cuda and self.fused_params() is not None):
+            # deferred: GenDR.forward runs the lighting kernel (or .textures materialises it with lit_textures)
+            return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,
+                        _pending_light=copy.deepcopy(self))
+        return Mesh(mesh.vertices, mesh.faces, self.lit_textures(mesh), mesh.texture_res, mesh.texture_type)

@@ -1,6 +1,13 @@
 """`Mesh` container: vertices [B,V,3], faces [B,F,3] int, textures [B,F,R*R,3] (surface) or [B,V,3] (vertex).
-API mirror of gendr.Mesh (/root/reference/gendr/mesh.py:14-126) minus OBJ texture I/O and voxelisation (asset
-pipeline / evaluation-only, out of the hot-path scope).
+API mirror of gendr.Mesh (/root/reference/gendr/mesh.py:14-126) minus OBJ texture I/O (asset pipeline, out of scope).
+
+Deferred scene steps.  The reference's scripts always run
+`mesh = lighting(mesh); mesh = transform(mesh); images = renderer(mesh)` (experiments/opt_shape.py:257-259).  On CUDA
+meshes `Lighting` and `LookAt`/`Look` do not execute their ~30 small torch kernels right away: they return a Mesh that
+remembers the step (`_pending_light`, `_pending_camera`), and `GenDR.forward` then runs lighting + camera + gather +
+rasterizer as one fused CUDA path (functional.render_scene).  Anything else that looks at the mesh first -- `.vertices`,
+`.textures`, `.face_vertices`, normals -- materialises the pending steps with the plain torch implementation, so the
+observable semantics are unchanged.  `gendr_b200.mesh.FUSE_SCENE = False` switches the deferral off.
 """
 import numpy as np
 import torch
@@ -9,12 +16,17 @@ import torch.nn.functional as F
 from . import functional
 
 
+FUSE_SCENE = True
+
+
 def _default_device():
     return torch.device('cuda') if torch.cuda.is_available() else torch.device('cpu')
 
 
 class Mesh(object):
-    def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type='surface'):
+    def __init__(self, vertices, faces, textures=None, texture_res=1, texture_type='surface', _pending_light=None,
+                 _pending_camera=None):
+        self._pending_light, self._pending_camera = _pending_light, _pending_camera
         if isinstance(vertices, np.ndarray):
             vertices = torch.from_numpy(vertices).float().to(_default_device())
         if isinstance(faces, np.ndarray):
@@ -50,9 +62,27 @@ class Mesh(object):
         dev = _default_device()
         return cls(vertices.to(dev), faces.to(dev), None, texture_res, texture_type)
 
+    def _materialize(self):
+        """Run the deferred lighting / camera steps with their torch implementations (lighting first: it needs the
+        world-space normals)."""
+        light, camera = self._pending_light, self._pending_camera
+        self._pending_light = self._pending_camera = None      # first: lit_textures() reads .vertices (world space) itself
+        if light is not None:
+            self._textures = light.lit_textures(self)
+        if camera is not None:
+            self._vertices = camera.transform(self._vertices)
+
     faces = property(lambda self: self._faces)
-    vertices = property(lambda self: self._vertices)
-    textures = property(lambda self: self._textures)
+
+    @property
+    def vertices(self):
+        self._materialize()
+        return self._vertices
+
+    @property
+    def textures(self):
+        self._materialize()
+        return self._textures
 
     @property
     def face_vertices(self):

@@ -4,7 +4,6 @@ plain mutable attribute read at call time (scripts change them between calls, e.
 `forward(mesh)` and `forward_tensors(face_vertices, face_textures)`, 2x supersampling + avg_pool2d anti-aliasing.
 """
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import functional
 
@@ -30,19 +29,25 @@ class GenDR(nn.Module):
         for name in _RENDER_ARGS:
             setattr(self, name, values[name])
 
+    def _render_args(self):
+        """image_size is doubled under anti-aliasing (renderer.py:68); the 2x2 average-pooling that follows in the
+        reference (renderer.py:92-93) is fused into the kernels (anti_aliasing=True; bit-identical)."""
+        args = {name: getattr(self, name) for name in _RENDER_ARGS}
+        args['image_size'] = self.image_size * (2 if self.anti_aliasing else 1)
+        args['anti_aliasing'] = bool(self.anti_aliasing)
+        return args
+
     def forward_tensors(self, face_vertices, face_textures):
-        size = self.image_size * (2 if self.anti_aliasing else 1)
-        images = functional.render(face_vertices=face_vertices, textures=face_textures, image_size=size,
-                                   **{name: getattr(self, name) for name in _RENDER_ARGS})
-        if self.anti_aliasing:
-            images = F.avg_pool2d(images, kernel_size=2, stride=2)
-        return images
+        return functional.render(face_vertices=face_vertices, textures=face_textures, **self._render_args())
 
     def forward(self, mesh):
+        if mesh.texture_type == 'surface' and mesh._pending_camera is not None:
+            # Lighting -> LookAt/Look were deferred by the mesh (gendr_b200/mesh.py): one fused scene node
+            camera = mesh._pending_camera
+            lighting = mesh._pending_light.fused_params() if mesh._pending_light is not None else None
+            return functional.render_scene(mesh._vertices, mesh.faces, mesh._textures, camera._fusable_eye(mesh),
+                                           camera=camera._fused_camera(), lighting=lighting, **self._render_args())
         if mesh.texture_type == 'surface' and getattr(self, 'fused_gather', True):
             # indexed path: vertices[faces] gather and its scatter-add backward run inside the CUDA kernels
-            size = self.image_size * (2 if self.anti_aliasing else 1)
-            images = functional.render_indexed(mesh.vertices, mesh.faces, mesh.textures, image_size=size,
-                                               **{name: getattr(self, name) for name in _RENDER_ARGS})
-            return F.avg_pool2d(images, kernel_size=2, stride=2) if self.anti_aliasing else images
+            return functional.render_indexed(mesh.vertices, mesh.faces, mesh.textures, **self._render_args())
         return self.forward_tensors(mesh.face_vertices, mesh.face_textures)

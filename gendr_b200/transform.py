@@ -1,4 +1,5 @@
 """Camera transforms as nn.Modules mapping Mesh -> Mesh (API mirror of gendr/transform.py:47-168)."""
+import copy
 import math
 
 import numpy as np
@@ -6,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import functional
+from . import mesh as _mesh
 from .functional import orthogonal, perspective  # noqa: F401  (re-exported like the reference module)
 from .mesh import Mesh
 
@@ -36,6 +38,29 @@ class _EyeCamera(Transform):
             return functional.perspective(vertices, angle=self.viewing_angle)
         return functional.orthogonal(vertices, scale=self.viewing_scale)
 
+    def _fusable_eye(self, mesh):
+        """The eye as something the fused camera kernel takes ([3] list/tuple or a [B,3] / [3] tensor without grad)."""
+        eye = self._eye
+        if isinstance(eye, np.ndarray):
+            eye = torch.from_numpy(eye)
+        if torch.is_tensor(eye):
+            if eye.requires_grad or eye.ndimension() not in (1, 2) or eye.shape[-1] != 3:
+                return None                                  # camera optimisation (experiments/opt_camera.py): torch path
+            if eye.ndimension() == 2 and eye.shape[0] != mesh.batch_size:
+                return None
+            return eye
+        if isinstance(eye, (list, tuple)) and len(eye) == 3 and all(isinstance(x, (int, float)) for x in eye):
+            return eye
+        return None
+
+    def forward(self, mesh):
+        if (_mesh.FUSE_SCENE and mesh._pending_camera is None and mesh._vertices.is_cuda and mesh.texture_type == 'surface'
+                and self._fusable_eye(mesh) is not None and self._fused_camera() is not None):
+            # deferred: GenDR.forward runs the camera kernel (or .vertices materialises it with transform())
+            return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,
+                        _pending_light=mesh._pending_light, _pending_camera=copy.copy(self))
+        return super().forward(mesh)
+
 
 class LookAt(_EyeCamera):
     """transform.py:109-138"""
@@ -44,6 +69,9 @@ class LookAt(_EyeCamera):
 
     def transform(self, vertices):
         return self._project(functional.look_at(vertices, self._eye))
+
+    def _fused_camera(self):
+        return dict(mode='look_at', perspective=self.perspective, viewing_angle=self.viewing_angle, viewing_scale=self.viewing_scale)
 
 
 class Look(_EyeCamera):
@@ -54,6 +82,13 @@ class Look(_EyeCamera):
 
     def transform(self, vertices):
         return self._project(functional.look(vertices, self._eye, self.camera_direction))
+
+    def _fused_camera(self):
+        d = self.camera_direction
+        if not (isinstance(d, (list, tuple)) and len(d) == 3 and all(isinstance(x, (int, float)) for x in d)):
+            return None
+        return dict(mode='look', perspective=self.perspective, viewing_angle=self.viewing_angle, viewing_scale=self.viewing_scale,
+                    direction=tuple(d))
 
 
 class Projection(Transform):

@@ -55,7 +55,7 @@ typedef struct gendr_render_params {
     float background[3];
 } gendr_render_params;
 
-/* Scratch the library needs between forward and backward: per-face records (144 B) + packed pixel rects (8 B). */
+/* Scratch the library needs between forward and backward: per-face records (176 B) + packed pixel rects (8 B). */
 size_t gendr_workspace_bytes(int batch, int faces);
 
 /* Forward.  background_prefilled != 0: read the background from soft_colors' RGB planes exactly as the reference
@@ -78,16 +78,85 @@ int gendr_backward_render(const float* faces, const float* textures, const float
  * (gendr/functional/face_vertices.py:9-27, called from gendr/mesh.py:102) into the face preprocessing and its backward
  * (a scatter-add into the vertex gradient) into the backward kernel, so the [B,F,3,3] face-vertex tensor and its
  * gradient are never materialised.  vertices [B,V,3] screen space; face_index int32 [B,F,3], or [F,3] when
- * index_shared != 0; indices are clamped to [0, V-1].  The backward must follow the forward on the same workspace. */
+ * index_shared != 0; indices are clamped to [0, V-1].  The backward must follow the forward on the same workspace.
+ * pooled_colors (may be NULL) / grad_is_pooled: fused 2x anti-aliasing, see gendr_forward_render_aa. */
 int gendr_forward_render_indexed(const float* vertices, const int* face_index, int index_shared, const float* textures,
-                                 float* aggrs_info, float* soft_colors, int batch, int num_vertices, int num_faces,
-                                 int texture_size, const gendr_render_params* params, void* workspace,
+                                 float* aggrs_info, float* soft_colors, float* pooled_colors, int batch, int num_vertices,
+                                 int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
                                  size_t workspace_bytes, void* stream);
 int gendr_backward_render_indexed(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
                                   const float* aggrs_info, float* grad_vertices, float* grad_textures,
-                                  const float* grad_soft_colors, int batch, int num_vertices, int num_faces,
-                                  int texture_size, const gendr_render_params* params, int zero_grads, void* workspace,
-                                  size_t workspace_bytes, void* stream);
+                                  const float* grad_soft_colors, int grad_is_pooled, int batch, int num_vertices,
+                                  int num_faces, int texture_size, const gendr_render_params* params, int zero_grads,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused 2x anti-aliasing.  The reference renders at 2S and then calls
+ * F.avg_pool2d(images, kernel_size=2, stride=2) (gendr/renderer.py:68,92-93,96,121-122).  Here params->image_size is the
+ * supersampled side (even); the forward kernel's epilogue additionally writes pooled_colors [B,4,S/2,S/2] -- summed in
+ * torch's order, so bit-identical to the unfused pooling -- and the backward kernel reads the cotangent of the POOLED
+ * image, grad_pooled_colors [B,4,S/2,S/2] (avg_pool2d's backward, grad/4 per pixel, happens in its prologue).
+ * soft_colors [B,4,S,S] (full resolution) is still written: the backward pass needs it. */
+int gendr_forward_render_aa(const float* faces, const float* textures, float* aggrs_info, float* soft_colors,
+                            float* pooled_colors, int batch, int num_faces, int texture_size,
+                            const gendr_render_params* params, void* workspace, size_t workspace_bytes, void* stream);
+int gendr_backward_render_aa(const float* faces, const float* textures, const float* soft_colors, const float* aggrs_info,
+                             float* grad_faces, float* grad_textures, const float* grad_pooled_colors, int batch,
+                             int num_faces, int texture_size, const gendr_render_params* params, int workspace_valid,
+                             int zero_grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Camera transform and lighting as CUDA kernels, with their backward passes.
+ *   gendr_camera_*    replace  gendr.functional.look_at / look (gendr/functional/look_at.py:11-68, look.py:11-56) followed by
+ *                     perspective / orthogonal (gendr/transform.py:14-44), i.e. LookAt.transform / Look.transform
+ *                     (transform.py:132-138, :161-168) and what autograd derives for them
+ *   gendr_lighting_*  replace  gendr.Lighting.forward for surface textures (gendr/lighting.py:48-58: ambient + one
+ *                     directional light from the face normal, gendr/mesh.py:104-108) and its autograd backward
+ * eyes: device [B,3] (eyes_batched != 0) or [3].  All buffers fp32 device memory except face_index (int32). */
+typedef struct gendr_camera_params {
+    int   mode;               /* 0 = look_at (camera looks from eye to at_or_direction), 1 = look (along at_or_direction) */
+    int   perspective;        /* 1 = perspective(viewing_angle), 0 = orthogonal(viewing_scale) */
+    float viewing_angle;      /* degrees, transform.py:14 */
+    float viewing_scale;      /* transform.py:32 */
+    float at_or_direction[3];
+    float up[3];
+} gendr_camera_params;
+typedef struct gendr_light_params {
+    float intensity_ambient;      float color_ambient[3];       /* lighting.py:38 */
+    float intensity_directional;  float color_directional[3];   /* lighting.py:39 */
+    float direction[3];                                          /* lighting.py:40 */
+} gendr_light_params;
+
+int gendr_camera_forward(const float* vertices, const float* eyes, int eyes_batched, float* screen_vertices, int batch,
+                         int num_vertices, const gendr_camera_params* camera, void* stream);
+/* grad_vertices [B,V,3] is overwritten (no zero-fill needed) */
+int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_batched, const float* grad_screen_vertices,
+                          float* grad_vertices, int batch, int num_vertices, const gendr_camera_params* camera, void* stream);
+int gendr_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                           float* lit_textures, int batch, int num_vertices, int num_faces, int texture_size,
+                           const gendr_light_params* light, void* stream);
+/* grad_textures [B,F,T,3] is overwritten (may be NULL); the normal's gradient is ADDED to grad_vertices (may be NULL) */
+int gendr_lighting_backward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                            const float* grad_lit_textures, float* grad_textures, float* grad_vertices, int batch,
+                            int num_vertices, int num_faces, int texture_size, const gendr_light_params* light, void* stream);
+
+/* The whole scene step in one call: world-space mesh -> Lighting -> LookAt/Look -> GenDR (the order every script of the
+ * reference uses: experiments/opt_shape.py:257-259, train_reconstruction.py:228-230), surface textures.
+ * Forward: camera kernel, lighting kernel, indexed face preprocessing, render kernel (4 launches; the reference issues ~40).
+ * Backward: render backward (scatter-adds into the screen-space vertex gradient and the lit-texture gradient held in the
+ * workspace), camera backward, lighting backward -> grad_vertices [B,V,3] w.r.t. the WORLD-space vertices and
+ * grad_textures [B,F,T,3] w.r.t. the UNLIT textures (may be NULL).  light may be NULL (no lighting step).
+ * pooled_colors / grad_is_pooled as in gendr_forward_render_aa. */
+size_t gendr_scene_workspace_bytes(int batch, int num_vertices, int num_faces, int texture_size);
+int gendr_scene_forward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                        const float* eyes, int eyes_batched, const gendr_camera_params* camera,
+                        const gendr_light_params* light, float* aggrs_info, float* soft_colors, float* pooled_colors,
+                        int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int gendr_scene_backward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                         const float* eyes, int eyes_batched, const gendr_camera_params* camera,
+                         const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
+                         const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures,
+                         int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* End-to-end convenience with HOST buffers (pinned or pageable): H2D copies of faces/textures/grad_soft_colors,
  * forward + backward on the current device, D2H copies of soft_colors/grad_faces/grad_textures, one stream

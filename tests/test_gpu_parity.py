@@ -268,13 +268,19 @@ def test_module_api_and_antialiasing(gpu_oracle):
     verts, faces = scenes.icosphere(2)
     mesh = gd.Mesh((verts * 0.5)[None].to(dev), faces[None].to(dev))
     mesh = gd.LookAt(viewing_angle=15)(gd.Lighting()(mesh))
+    assert mesh._pending_camera is not None and mesh._pending_light is not None      # deferred scene steps (gendr_b200/mesh.py)
     r = gd.GenDR(image_size=32, dist_func='logistic', dist_scale=0.02, anti_aliasing=True)
-    img = r(mesh)
-    assert img.shape == (1, 4, 32, 32)
+    img_fused = r(mesh)                     # fused scene path: camera + lighting + gather + render + 2x2 pooling
+    assert img_fused.shape == (1, 4, 32, 32)
+    mesh.vertices                           # materialise the pending steps with the torch implementation
+    assert mesh._pending_camera is None and mesh._pending_light is None
+    img = r(mesh)                           # indexed path on the materialised screen-space mesh, fused pooling
     r.anti_aliasing = False
     r.image_size = 64
     full = r.forward_tensors(mesh.face_vertices, mesh.face_textures)
-    assert torch.allclose(img, torch.nn.functional.avg_pool2d(full, 2, 2), atol=1e-6)
+    assert torch.equal(img, torch.nn.functional.avg_pool2d(full, 2, 2))
+    # default eye: the camera basis is the identity, so kernel and torch glue agree to the last bit of the light intensity
+    assert float((img_fused - img).abs().max()) <= 1e-6
     with pytest.raises(ValueError):
         gd.GenDR(aggr_rgb_func='median')
     with pytest.raises(KeyError):
