@@ -14,19 +14,23 @@ cp -r "$REF/gendr" "$DST/gendr"
 mkdir -p "$DST/data"; cp "$REF/experiments/data/sphere_642.obj" "$DST/data/"
 chmod -R u+w "$DST"
 cd "$DST"
-# a one-extension setup script (the reference's setup.py builds four; only one is on the hot path)
+# a two-extension setup script (the reference's setup.py builds four; the renderer is the hot path, the voxelizer is
+# SURVEY 8(f) row 4 -- the parity oracle for gendr_voxelize)
 cat > setup_renderer_only.py <<'PY'
 from setuptools import setup
 from torch.utils.cpp_extension import BuildExtension, CUDAExtension
 setup(name='gendr_ref_renderer',
       ext_modules=[CUDAExtension('gendr.cuda.generalized_renderer',
                                  ['gendr/cuda/generalized_renderer_cuda.cpp',
-                                  'gendr/cuda/generalized_renderer_cuda_kernel.cu'])],
+                                  'gendr/cuda/generalized_renderer_cuda_kernel.cu']),
+                   CUDAExtension('gendr.cuda.voxelization',
+                                 ['gendr/cuda/voxelization_cuda.cpp',
+                                  'gendr/cuda/voxelization_cuda_kernel.cu'])],
       cmdclass={'build_ext': BuildExtension})
 PY
 TORCH_CUDA_ARCH_LIST="10.0a" MAX_JOBS=8 python setup_renderer_only.py build_ext --inplace > build.log 2>&1 || { tail -30 build.log; exit 1; }
-# the three off-path extensions (texture asset I/O, voxelizer) are not built: empty stand-ins so `import gendr` works
-for m in load_textures create_texture_image voxelization; do
+# the two asset-I/O extensions are not built: empty stand-ins so `import gendr` works
+for m in load_textures create_texture_image; do
   [ -f gendr/cuda/$m.py ] || echo "# stand-in: extension not built (off the hot path)" > gendr/cuda/$m.py
 done
 ls -la gendr/cuda/*.so

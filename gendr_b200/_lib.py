@@ -55,6 +55,8 @@ SIGNATURES = {
     'gendr_scene_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
     'gendr_scene_forward': (_I, [_P, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
     'gendr_scene_backward': (_I, [_P, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_voxelize_workspace_bytes': (_SZ, [_I, _I]),
+    'gendr_voxelize': (_I, [_P, _P, _I, _I, _I, _P, _SZ, _P]),
     'gendr_render_forward_backward_host': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _PP]),
     'gendr_sigmoid_forward': (_F, [_I, _F, _F, _F, _F, _F]),
     'gendr_sigmoid_backward': (_F, [_I, _F, _F, _F, _F, _F]),

@@ -4,6 +4,7 @@
 #include "../../include/gendr_b200.h"
 #include "render_kernels.cuh"
 #include "scene_kernels.cuh"
+#include "voxel_kernels.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -756,6 +757,49 @@ int gendr_scene_backward(const float* vertices, const int* face_index, int index
         if (int e = lighting_backward_impl(L, vertices, face_index, index_shared, textures, w.grad_lit, grad_textures, grad_vertices, batch,
                                            num_vertices, num_faces, texture_size, st)) return e;
     }
+    return 0;
+}
+
+// ---- voxelizer ------------------------------------------------------------------------------
+static const size_t kVoxelSmemLimit = 160 * 1024;      // both bit masks of one batch item in shared memory up to here
+static size_t voxel_words(int vs) { return (size_t)vs * vs * ((vs + 31) / 32); }
+
+size_t gendr_voxelize_workspace_bytes(int batch, int voxel_size) {
+    if (batch < 0 || voxel_size < 1) return 0;
+    const size_t words = voxel_words(voxel_size);
+    const bool smem = 2 * words * 4 <= kVoxelSmemLimit;
+    return al256((size_t)batch * words * 4) + (smem ? 0 : al256((size_t)batch * 2 * words * 4)) + 256;
+}
+
+int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, int voxel_size, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    if (batch < 0 || num_faces < 0 || voxel_size < 1 || voxel_size > 1024) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_voxelize");
+    if ((long long)batch * voxel_size * voxel_size * voxel_size >= (1ll << 31) || (long long)batch * num_faces * 9 >= (1ll << 31))
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "gendr_voxelize: problem too large for 32-bit indexing");
+    if (batch == 0) return 0;
+    if ((!faces && num_faces > 0) || !voxels || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_voxelize");
+    if (workspace_bytes < gendr_voxelize_workspace_bytes(batch, voxel_size)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_voxelize_workspace_bytes)");
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(voxels), "selecting the device that owns `voxels`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int vs = voxel_size, W = (vs + 31) / 32;
+    const size_t words = voxel_words(vs);
+    const bool smem = 2 * words * 4 <= kVoxelSmemLimit;
+    uint32_t* mask = reinterpret_cast<uint32_t*>(workspace);
+    uint32_t* scratch = smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + al256((size_t)batch * words * 4));
+    GENDR_CUDA(cudaMemsetAsync(mask, 0, (size_t)batch * words * 4, st), "zero occupancy mask");
+    if (num_faces > 0) {
+        const int ray_blocks = (vs * vs + 255) / 256;
+        voxel_surface_kernel<<<(unsigned)(batch * 3 * ray_blocks), 256, 0, st>>>(faces, mask, batch, num_faces, vs, W, ray_blocks);
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "voxel_surface_kernel launch");
+    }
+    const size_t smem_bytes = smem ? 2 * words * 4 : 0;
+    if (smem_bytes > 48 * 1024)
+        GENDR_CUDA(cudaFuncSetAttribute(voxel_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), "voxel_fill_kernel smem");
+    voxel_fill_kernel<<<(unsigned)batch, VOX_FILL_THREADS, smem_bytes, st>>>(faces, mask, scratch, voxels, num_faces, vs, W, smem ? 1 : 0);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "voxel_fill_kernel launch");
     return 0;
 }
 

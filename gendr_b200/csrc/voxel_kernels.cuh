@@ -1,0 +1,171 @@
+// voxel_kernels.cuh -- the voxelizer, rebuilt for sm_100a.
+//
+// Replaces gendr.functional.voxelization(faces, size, normalize=False) (/root/reference/gendr/functional/voxelization.py:45-62),
+// i.e. the reference's four kernels (/root/reference/gendr/cuda/voxelization_cuda_kernel.cu: sub1 :36-93 ray casting along
+// one axis, sub2 :96-124 vertex voxels, sub3 :126-149 + sub4 :151-194 flood fill of the outside) and the Python loop around
+// them: 3 sub1 launches on permuted copies of the faces, sub2, 3 tensor adds + a compare, sub3, and then sub4 + TWO .sum()
+// host synchronisations per flood-fill sweep until nothing changes (typically 30-60 sweeps).
+//
+// Here: TWO launches and no host synchronisation.
+//   voxel_surface_kernel  one CTA = 256 rays of one (batch item, axis); faces are staged through shared memory 256 at a time
+//                         as per-face constants (edge vectors, determinant), so the all-pairs ray x face loop reads them as
+//                         broadcast LDS.128; hits set bits in a packed occupancy mask (1 bit per voxel) with atomicOr.
+//                         Grid = B * 3 * ceil(vs^2 / 256) CTAs.
+//   voxel_fill_kernel     one CTA per batch item: the whole volume lives in shared memory as bit masks (vs = 32: 2 x 4 KB);
+//                         vertex voxels are OR-ed in, the outside is flood-filled with word-parallel bit operations (32 voxels
+//                         per instruction, chaotic iteration until a sweep changes nothing, __syncthreads_or), and the int32
+//                         result [vs,vs,vs] = 1 - visible is written coalesced.
+//
+// Results are integers and BIT-IDENTICAL to the reference's CUDA kernels: the ray/face arithmetic reproduces the operation
+// DAG nvcc emitted for the reference on sm_100a (read from its SASS; oracle/gendr_voxel_oracle.c mode 1):
+//     det = fma(x1d, y2d, -(y1d*x2d));  t1 = fma(y2d, xpd, -(x2d*ypd)) / det;  t2 = fma(x1d, ypd, -(y1d*xpd)) / det
+//     zi  = floor(face[2] + fma(z1d, t1, z2d*t2))        (IEEE division; F2I.FLOOR saturating, NaN -> 0)
+// and the flood fill is a monotone fixed point (the empty voxels 6-connected to an empty boundary voxel), independent of
+// the update order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gendr {
+
+constexpr int VOX_CHUNK = 256;          // faces staged per shared-memory chunk
+constexpr int VOX_FILL_THREADS = 1024;
+
+// word index of voxel (c0, c1, c2) in the packed mask of one batch item: [c0][c1][W] words, bit = c2 & 31
+__device__ __forceinline__ int vox_word(int c0, int c1, int c2, int vs, int W) { return (c0 * vs + c1) * W + (c2 >> 5); }
+
+__global__ void __launch_bounds__(256) voxel_surface_kernel(const float* __restrict__ faces, uint32_t* __restrict__ mask, int B, int F,
+                                                            int vs, int W, int ray_blocks) {
+    __shared__ float4 fc[VOX_CHUNK][3];     // per face: (f0 f1 f2 y1d) (x1d z1d y2d x2d) (z2d det sdet -)
+    const int tid = threadIdx.x;
+    int blk = blockIdx.x;
+    const int rb = blk % ray_blocks; blk /= ray_blocks;
+    const int axis = blk % 3;
+    const int b = blk / 3;
+    // voxelization.py:14-19: dim 0 -> faces[..., [2,1,0]], dim 1 -> faces[..., [0,2,1]], dim 2 -> as is; results transposed back
+    const int yr = (axis == 0) ? 2 : 0, xr = (axis == 2) ? 1 : ((axis == 0) ? 1 : 2), zr = (axis == 0) ? 0 : ((axis == 1) ? 1 : 2);
+    const int ray = rb * 256 + tid;
+    const bool active = ray < vs * vs;
+    const int y = ray % vs, x = (ray / vs) % vs;                 // :50-51
+    const float yf = (float)y, xf = (float)x, fvs = (float)vs;
+    uint32_t* m = mask + (size_t)b * vs * vs * W;
+
+    for (int f0 = 0; f0 < F; f0 += VOX_CHUNK) {
+        const int nf = min(VOX_CHUNK, F - f0);
+        __syncthreads();
+        if (tid < nf) {
+            const float* f = faces + ((size_t)b * F + f0 + tid) * 9;
+            float v[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = __fmul_rn(__ldg(f + k), fvs);          // voxelization.py:50  faces *= size
+            const float a0 = v[yr], a1 = v[xr], a2 = v[zr];
+            const float y1d = __fsub_rn(v[3 + yr], a0), x1d = __fsub_rn(v[3 + xr], a1), z1d = __fsub_rn(v[3 + zr], a2);
+            const float y2d = __fsub_rn(v[6 + yr], a0), x2d = __fsub_rn(v[6 + xr], a1), z2d = __fsub_rn(v[6 + zr], a2);
+            const float det = __fmaf_rn(x1d, y2d, -__fmul_rn(y1d, x2d));
+            // sign of det for the exact-safe early rejection below; 0 disables it (|det| outside [2^-60, 2^60], 0 or NaN)
+            const float ad = fabsf(det);
+            const float sdet = (ad > 8.6736174e-19f && ad < 1.1529215e18f) ? copysignf(1.f, det) : 0.f;
+            fc[tid][0] = make_float4(a0, a1, a2, y1d);
+            fc[tid][1] = make_float4(x1d, z1d, y2d, x2d);
+            fc[tid][2] = make_float4(z2d, det, sdet, 0.f);
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int j = 0; j < nf; ++j) {
+            const float4 A = fc[j][0], Bq = fc[j][1], Cq = fc[j][2];
+            const float det = Cq.y;
+            if (det == 0.f) continue;                                                    // :66
+            const float ypd = __fsub_rn(yf, A.x), xpd = __fsub_rn(xf, A.y);              // :63-64
+            const float n1 = __fmaf_rn(Bq.z, xpd, -__fmul_rn(Bq.w, ypd));                // y2d*xpd - x2d*ypd
+            // Early rejection, exact: with |det| <= 2^60 a numerator of the wrong sign and magnitude > 1e-20 gives a quotient
+            // that is negative and non-zero (>= 8e-39 in magnitude), i.e. `t < 0` in the reference (:69-70).
+            if (n1 * Cq.z < -1e-20f) continue;
+            const float n2 = __fmaf_rn(Bq.x, ypd, -__fmul_rn(A.w, xpd));                 // -y1d*xpd + x1d*ypd
+            if (n2 * Cq.z < -1e-20f) continue;
+            const float t1 = __fdiv_rn(n1, det), t2 = __fdiv_rn(n2, det);                // :67-68
+            if (t1 < 0.f) continue;
+            if (t2 < 0.f) continue;
+            if (1.f < __fadd_rn(t1, t2)) continue;                                       // :71
+            const int zi = __float2int_rd(__fadd_rn(A.z, __fmaf_rn(Bq.y, t1, __fmul_rn(Cq.x, t2))));   // :72
+            if (zi < 0 || zi >= vs) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                                                // :73-92: the four voxels around the ray
+                const int yi = y - (q & 1), xi = x - (q >> 1);
+                if (yi < 0 || xi < 0) continue;
+                int c[3];
+                c[yr] = yi; c[xr] = xi; c[zr] = zi;
+                atomicOr(m + vox_word(c[0], c[1], c[2], vs, W), 1u << (c[2] & 31));
+            }
+        }
+    }
+}
+
+// occ / vis: bit masks of one batch item, in shared memory when they fit, else in global scratch (generic pointers)
+__global__ void __launch_bounds__(VOX_FILL_THREADS) voxel_fill_kernel(const float* __restrict__ faces, const uint32_t* __restrict__ mask,
+                                                                      uint32_t* __restrict__ scratch, int32_t* __restrict__ voxels, int F,
+                                                                      int vs, int W, int use_smem) {
+    extern __shared__ uint32_t vox_smem[];
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const int rows = vs * vs, words = rows * W;
+    volatile uint32_t* occ = use_smem ? vox_smem : scratch + (size_t)b * 2 * words;
+    volatile uint32_t* vis = occ + words;
+    const uint32_t* m = mask + (size_t)b * words;
+    for (int i = tid; i < words; i += VOX_FILL_THREADS) occ[i] = m[i];
+    __syncthreads();
+    // sub2 (:96-124): the voxel containing each vertex
+    const float fvs = (float)vs;
+    for (int v = tid; v < F * 3; v += VOX_FILL_THREADS) {
+        const float* p = faces + ((size_t)b * F * 3 + v) * 3;
+        const int c0 = __float2int_rd(__fmul_rn(__ldg(p), fvs)), c1 = __float2int_rd(__fmul_rn(__ldg(p + 1), fvs)),
+                  c2 = __float2int_rd(__fmul_rn(__ldg(p + 2), fvs));
+        if (c0 >= 0 && c0 < vs && c1 >= 0 && c1 < vs && c2 >= 0 && c2 < vs)
+            atomicOr(const_cast<uint32_t*>(occ) + vox_word(c0, c1, c2, vs, W), 1u << (c2 & 31));
+    }
+    __syncthreads();
+    // sub3 (:126-149): empty boundary voxels are visible
+    for (int i = tid; i < words; i += VOX_FILL_THREADS) {
+        const int row = i / W, w = i - row * W, c0 = row / vs, c1 = row - c0 * vs;
+        const int nbits = min(32, vs - 32 * w);
+        const uint32_t valid = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+        const uint32_t fr = ~occ[i] & valid;
+        uint32_t edge = 0;
+        if (c0 == 0 || c0 == vs - 1 || c1 == 0 || c1 == vs - 1) edge = valid;
+        else {
+            if (w == 0) edge |= 1u;
+            if ((vs - 1) >> 5 == w) edge |= 1u << ((vs - 1) & 31);
+        }
+        vis[i] = fr & edge;
+    }
+    __syncthreads();
+    // sub4 until stable (:151-194 + voxelization.py:37-42): an empty interior voxel next to a visible voxel becomes visible.
+    // Chaotic iteration on monotone bit sets: stale reads are harmless, a sweep without any write is the fixed point.
+    for (;;) {
+        int changed = 0;
+        for (int row = tid; row < rows; row += VOX_FILL_THREADS) {
+            const int c0 = row / vs, c1 = row - c0 * vs;
+            if (c0 == 0 || c0 == vs - 1 || c1 == 0 || c1 == vs - 1) continue;
+            for (int w = 0; w < W; ++w) {
+                const int i = row * W + w;
+                const int nbits = min(32, vs - 32 * w);
+                const uint32_t valid = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+                const uint32_t fr = ~occ[i] & valid;
+                const uint32_t v = vis[i];
+                uint32_t nb = vis[i - vs * W] | vis[i + vs * W] | vis[i - W] | vis[i + W];
+                if (w > 0) nb |= vis[i - 1] >> 31;
+                if (w + 1 < W) nb |= vis[i + 1] << 31;
+                uint32_t s = v | (fr & nb), old;
+                do { old = s; s |= fr & ((s << 1) | (s >> 1)); } while (s != old);      // along c2 inside the word
+                if (s != v) { vis[i] = s; changed = 1; }
+            }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // 1 - visible (voxelization.py:43), int32 [vs,vs,vs], coalesced along c2
+    int32_t* out = voxels + (size_t)b * rows * vs;
+    for (int i = tid; i < rows * vs; i += VOX_FILL_THREADS) {
+        const int row = i / vs, c2 = i - row * vs;
+        out[i] = 1 - (int)((vis[row * W + (c2 >> 5)] >> (c2 & 31)) & 1u);
+    }
+}
+
+}  // namespace gendr

@@ -104,3 +104,8 @@ class Mesh(object):
         if self.texture_type == 'vertex':
             return functional.face_vertices(self.textures, self.faces)
         raise ValueError('texture type not applicable')
+
+    def voxelize(self, voxel_size=32):
+        """gendr/mesh.py:124-126"""
+        face_vertices_norm = self.face_vertices * voxel_size / (voxel_size - 1) + 0.5
+        return functional.voxelization(face_vertices_norm, voxel_size, False)

@@ -158,6 +158,16 @@ int gendr_scene_backward(const float* vertices, const int* face_index, int index
                          int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* Voxelizer: replaces gendr.functional.voxelization(faces, size, normalize=False)
+ * (gendr/functional/voxelization.py:45-62) -- the pybind functions voxelize_sub1..4 of gendr/cuda/voxelization_cuda.cpp:85-88,
+ * the three axis permutations, the threshold and the host loop with two .sum() synchronisations per flood-fill sweep -- by
+ * two launches without any host synchronisation.  faces [B,F,3,3] fp32 in unit-cube coordinates (what Mesh.voxelize passes,
+ * gendr/mesh.py:124-126; scaled by voxel_size inside), voxels int32 [B,vs,vs,vs] (1 = surface or inside, 0 = outside),
+ * fully overwritten.  Bit-identical to the reference's CUDA kernels. */
+size_t gendr_voxelize_workspace_bytes(int batch, int voxel_size);
+int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, int voxel_size, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* End-to-end convenience with HOST buffers (pinned or pageable): H2D copies of faces/textures/grad_soft_colors,
  * forward + backward on the current device, D2H copies of soft_colors/grad_faces/grad_textures, one stream
  * synchronisation at the end.  Device scratch is cached inside the library between calls. */

@@ -137,3 +137,29 @@ DIST_SWEEP = [('hard', {}), ('uniform', {}), ('cubic_hermite', {}), ('wigner_sem
               ('gamma', dict(dist_shape=2.0)), ('gamma_rev', dict(dist_shape=2.0)), ('levy', {}), ('levy_rev', {})]
 TCN_SWEEP = [('hard', None), ('max', None), ('probabilistic', None), ('einstein', None), ('hamacher', 0.5), ('frank', 2.0),
              ('yager', 2.0), ('aczel_alsina', 2.0), ('dombi', 2.0), ('schweizer_sklar', -2.0)]
+
+
+def voxel_cases():
+    """Inputs for the voxelizer tests, as gendr.Mesh.voxelize passes them to
+    gendr.functional.voxelization: face_vertices * vs / (vs - 1) + 0.5 (gendr/mesh.py:124-126).
+      sphere32   jittered icosphere (320 faces), batch 3, 32^3 -- closed surfaces: the interior must fill
+      sphere40   the same mesh at 40^3 (two mask words per row, size not a multiple of 32)
+      soup16     open triangle soup partly outside the unit cube, 16^3 (nothing encloses anything; clipping at the borders)
+      flat24     axis-aligned and degenerate (zero-area) faces on exact lattice planes, 24^3 (det == 0 / t == 0 edge cases)"""
+    import numpy as np
+    verts, faces = icosphere(2)
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    v = (verts * 0.4)[None].repeat(B, 1, 1) * (1 + 0.2 * torch.rand(B, verts.shape[0], 1, generator=g))
+    fv = gd.functional.face_vertices(v, faces[None].repeat(B, 1, 1))
+    cases = {}
+    for name, vs in (('sphere32', 32), ('sphere40', 40)):
+        cases[name] = ((fv * vs / (vs - 1) + 0.5).numpy().astype(np.float32), vs)
+    soup = torch.rand(2, 60, 1, 3, generator=g) * 1.2 - 0.1 + (torch.rand(2, 60, 3, 3, generator=g) - 0.5) * 0.5
+    cases['soup16'] = (soup.numpy().astype(np.float32), 16)
+    flat = torch.tensor([[[0.25, 0.25, 0.5], [0.75, 0.25, 0.5], [0.25, 0.75, 0.5]],       # in the plane c2 = 12 (exact lattice plane)
+                         [[0.5, 0.125, 0.125], [0.5, 0.875, 0.125], [0.5, 0.5, 0.875]],     # in the plane c0 = 12
+                         [[0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [0.3, 0.3, 0.3]],               # degenerate: two equal vertices
+                         [[0.2, 0.6, 0.7], [0.4, 0.6, 0.7], [0.8, 0.6, 0.7]]])[None]        # degenerate: collinear
+    cases['flat24'] = (flat.numpy().astype(np.float32), 24)
+    return cases
