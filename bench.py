@@ -349,9 +349,11 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, F, S, T)
-    traffic = None
+    traffic, prof = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload, {}).get('backward_dram_bytes_per_launch')
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload, {})
+        if B == 64:          # the ncu capture is of the default per-GPU batch
+            traffic = prof.get('backward_dram_bytes_per_launch')
     except Exception:
         pass
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
@@ -363,6 +365,15 @@ def main():
                                'frac_of_measured': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
                                'frac_of_8TBps_nominal': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / 8000.0},
                 'note': 'all-pairs ALU/SFU-bound path: compulsory traffic is ~0.01 B per pixel*face (SURVEY 8d), so the HBM fraction is small by construction'}
+    if prof.get('backward_warp_instructions') and B == 64 and clocks.get('sm_mhz'):
+        # the roofline that actually binds: warp-instruction issue rate.  Instructions per launch from the committed
+        # ncu capture of this workload (smsp__inst_executed.sum), duration and SM clock measured live in this run.
+        peak_issue = 148 * 4 * clocks['sm_mhz'] * 1e6            # 148 SMs x 4 schedulers x 1 warp-instruction per clock
+        ach = prof['backward_warp_instructions'] / (bwd_ms * 1e-3)
+        roofline['issue_rate'] = {'bound': 'warp-instruction issue (FP32/SFU pipes)', 'achieved': ach / 1e9, 'peak': peak_issue / 1e9,
+                                  'unit': 'G warp-instr/s', 'frac': ach / peak_issue,
+                                  'active_lanes_per_instruction': prof.get('backward_active_lanes_per_instruction'),
+                                  'source': 'instructions: profiles/roofline_traffic.json (ncu); time and SM clock: this run'}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
