@@ -35,6 +35,16 @@ def allreduce_shared_face_grads(grad_faces, group=None):
     return total
 
 
+def allreduce_shared_vertex_grads(grad_vertices, group=None):
+    """grad_vertices [b_local, V, 3] (what the indexed / scene paths return) -> gradient w.r.t. the batch-shared vertices
+    [V, 3]: local batch sum + ONE all-reduce(SUM).  The payload is 6x smaller than the per-face form (51 KB instead of 295 KB at
+    V = 4225 / F = 8192)."""
+    total = grad_vertices.sum(dim=0)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total
+
+
 def gather_images(images, batch, group=None):
     """Reassemble the full [B,4,S,S] image batch on every rank from the rank-local slices (uneven slices allowed)."""
     world = dist.get_world_size(group)

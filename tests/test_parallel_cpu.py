@@ -53,7 +53,18 @@ def _worker(rank, world, port, out_dir):
     gf, _ = oracle.backward(f, parallel.shard_batch(g).numpy(), p)
     shared = parallel.allreduce_shared_face_grads(torch.from_numpy(gf).view(hi - lo, -1, 3, 3))
     images = parallel.gather_images(torch.from_numpy(f['soft_colors']), B)
+    # indexed / scene form of the same exchange: the gradient w.r.t. the batch-shared WORLD vertices [V,3] (camera backward of
+    # the rank's views, numpy scene oracle) is a local sum + one all-reduce
+    from oracle import scene_oracle as so
+    world_v = (verts * 0.5)[None].repeat(B, 1, 1).numpy()
+    eyes = scenes.orbit_eyes(B).numpy()
+    g_screen = torch.randn(B, verts.shape[0], 3, generator=torch.Generator().manual_seed(1)).numpy()
+    gv_local = so.camera_backward(world_v[lo:hi], eyes[lo:hi], g_screen[lo:hi], viewing_angle=15., dtype=np.float32)
+    shared_v = parallel.allreduce_shared_vertex_grads(torch.from_numpy(np.ascontiguousarray(gv_local, np.float32)))
     if rank == 0:
+        want_v = so.camera_backward(world_v, eyes, g_screen, viewing_angle=15., dtype=np.float32).sum(0)
+        assert np.allclose(shared_v.numpy(), want_v, rtol=1e-5, atol=1e-5 * np.abs(want_v).max()), 'shared vertex gradient'
+
         full = oracle.forward(fv.numpy(), ft.numpy(), p)
         gfull, _ = oracle.backward(full, g.numpy(), p)
         ok_img = bool(np.array_equal(images.numpy(), full['soft_colors']))
