@@ -761,14 +761,14 @@ int gendr_scene_backward(const float* vertices, const int* face_index, int index
 }
 
 // ---- voxelizer ------------------------------------------------------------------------------
-static const size_t kVoxelSmemLimit = 160 * 1024;      // both bit masks of one batch item in shared memory up to here
+static const size_t kVoxelSmemLimit = 160 * 1024;      // the three bit masks of one batch item in shared memory up to here
 static size_t voxel_words(int vs) { return (size_t)vs * vs * ((vs + 31) / 32); }
 
 size_t gendr_voxelize_workspace_bytes(int batch, int voxel_size) {
     if (batch < 0 || voxel_size < 1) return 0;
     const size_t words = voxel_words(voxel_size);
-    const bool smem = 2 * words * 4 <= kVoxelSmemLimit;
-    return al256((size_t)batch * words * 4) + (smem ? 0 : al256((size_t)batch * 2 * words * 4)) + 256;
+    const bool smem = 3 * words * 4 <= kVoxelSmemLimit;
+    return al256((size_t)batch * words * 4) + (smem ? 0 : al256((size_t)batch * 3 * words * 4)) + 256;
 }
 
 int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, int voxel_size, void* workspace, size_t workspace_bytes,
@@ -784,7 +784,7 @@ int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, in
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int vs = voxel_size, W = (vs + 31) / 32;
     const size_t words = voxel_words(vs);
-    const bool smem = 2 * words * 4 <= kVoxelSmemLimit;
+    const bool smem = 3 * words * 4 <= kVoxelSmemLimit;
     uint32_t* mask = reinterpret_cast<uint32_t*>(workspace);
     uint32_t* scratch = smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + al256((size_t)batch * words * 4));
     GENDR_CUDA(cudaMemsetAsync(mask, 0, (size_t)batch * words * 4, st), "zero occupancy mask");
@@ -794,7 +794,7 @@ int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, in
         g_launches++;
         GENDR_CUDA(cudaGetLastError(), "voxel_surface_kernel launch");
     }
-    const size_t smem_bytes = smem ? 2 * words * 4 : 0;
+    const size_t smem_bytes = smem ? 3 * words * 4 : 0;
     if (smem_bytes > 48 * 1024)
         GENDR_CUDA(cudaFuncSetAttribute(voxel_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes), "voxel_fill_kernel smem");
     voxel_fill_kernel<<<(unsigned)batch, VOX_FILL_THREADS, smem_bytes, st>>>(faces, mask, scratch, voxels, num_faces, vs, W, smem ? 1 : 0);

@@ -11,9 +11,9 @@
 //                         as per-face constants (edge vectors, determinant), so the all-pairs ray x face loop reads them as
 //                         broadcast LDS.128; hits set bits in a packed occupancy mask (1 bit per voxel) with atomicOr.
 //                         Grid = B * 3 * ceil(vs^2 / 256) CTAs.
-//   voxel_fill_kernel     one CTA per batch item: the whole volume lives in shared memory as bit masks (vs = 32: 2 x 4 KB);
+//   voxel_fill_kernel     one CTA per batch item: the whole volume lives in shared memory as bit masks (vs = 32: 3 x 4 KB);
 //                         vertex voxels are OR-ed in, the outside is flood-filled with word-parallel bit operations (32 voxels
-//                         per instruction, chaotic iteration until a sweep changes nothing, __syncthreads_or), and the int32
+//                         per instruction, double-buffered sweeps until one changes nothing, __syncthreads_or), and the int32
 //                         result [vs,vs,vs] = 1 - visible is written coalesced.
 //
 // Results are integers and BIT-IDENTICAL to the reference's CUDA kernels: the ray/face arithmetic reproduces the operation
@@ -100,15 +100,16 @@ __global__ void __launch_bounds__(256) voxel_surface_kernel(const float* __restr
     }
 }
 
-// occ / vis: bit masks of one batch item, in shared memory when they fit, else in global scratch (generic pointers)
+// occ / visA / visB: bit masks of one batch item, in shared memory when they fit, else in global scratch (generic pointers)
 __global__ void __launch_bounds__(VOX_FILL_THREADS) voxel_fill_kernel(const float* __restrict__ faces, const uint32_t* __restrict__ mask,
                                                                       uint32_t* __restrict__ scratch, int32_t* __restrict__ voxels, int F,
                                                                       int vs, int W, int use_smem) {
     extern __shared__ uint32_t vox_smem[];
     const int tid = threadIdx.x, b = blockIdx.x;
     const int rows = vs * vs, words = rows * W;
-    volatile uint32_t* occ = use_smem ? vox_smem : scratch + (size_t)b * 2 * words;
-    volatile uint32_t* vis = occ + words;
+    uint32_t* occ = use_smem ? vox_smem : scratch + (size_t)b * 3 * words;
+    uint32_t* cur = occ + words;            // visible set read by the current sweep
+    uint32_t* nxt = cur + words;            // visible set written by the current sweep
     const uint32_t* m = mask + (size_t)b * words;
     for (int i = tid; i < words; i += VOX_FILL_THREADS) occ[i] = m[i];
     __syncthreads();
@@ -118,11 +119,10 @@ __global__ void __launch_bounds__(VOX_FILL_THREADS) voxel_fill_kernel(const floa
         const float* p = faces + ((size_t)b * F * 3 + v) * 3;
         const int c0 = __float2int_rd(__fmul_rn(__ldg(p), fvs)), c1 = __float2int_rd(__fmul_rn(__ldg(p + 1), fvs)),
                   c2 = __float2int_rd(__fmul_rn(__ldg(p + 2), fvs));
-        if (c0 >= 0 && c0 < vs && c1 >= 0 && c1 < vs && c2 >= 0 && c2 < vs)
-            atomicOr(const_cast<uint32_t*>(occ) + vox_word(c0, c1, c2, vs, W), 1u << (c2 & 31));
+        if (c0 >= 0 && c0 < vs && c1 >= 0 && c1 < vs && c2 >= 0 && c2 < vs) atomicOr(occ + vox_word(c0, c1, c2, vs, W), 1u << (c2 & 31));
     }
     __syncthreads();
-    // sub3 (:126-149): empty boundary voxels are visible
+    // sub3 (:126-149): empty boundary voxels are visible (both buffers: boundary rows never change afterwards)
     for (int i = tid; i < words; i += VOX_FILL_THREADS) {
         const int row = i / W, w = i - row * W, c0 = row / vs, c1 = row - c0 * vs;
         const int nbits = min(32, vs - 32 * w);
@@ -134,11 +134,12 @@ __global__ void __launch_bounds__(VOX_FILL_THREADS) voxel_fill_kernel(const floa
             if (w == 0) edge |= 1u;
             if ((vs - 1) >> 5 == w) edge |= 1u << ((vs - 1) & 31);
         }
-        vis[i] = fr & edge;
+        cur[i] = nxt[i] = fr & edge;
     }
     __syncthreads();
     // sub4 until stable (:151-194 + voxelization.py:37-42): an empty interior voxel next to a visible voxel becomes visible.
-    // Chaotic iteration on monotone bit sets: stale reads are harmless, a sweep without any write is the fixed point.
+    // Jacobi sweeps on two buffers (race-free): every sweep reads `cur` and writes `nxt`; along c2 a word is filled to its
+    // local fixed point (32 voxels per instruction).  The limit is the same monotone fixed point the reference reaches.
     for (;;) {
         int changed = 0;
         for (int row = tid; row < rows; row += VOX_FILL_THREADS) {
@@ -149,22 +150,24 @@ __global__ void __launch_bounds__(VOX_FILL_THREADS) voxel_fill_kernel(const floa
                 const int nbits = min(32, vs - 32 * w);
                 const uint32_t valid = nbits >= 32 ? 0xffffffffu : ((1u << nbits) - 1u);
                 const uint32_t fr = ~occ[i] & valid;
-                const uint32_t v = vis[i];
-                uint32_t nb = vis[i - vs * W] | vis[i + vs * W] | vis[i - W] | vis[i + W];
-                if (w > 0) nb |= vis[i - 1] >> 31;
-                if (w + 1 < W) nb |= vis[i + 1] << 31;
+                const uint32_t v = cur[i];
+                uint32_t nb = cur[i - vs * W] | cur[i + vs * W] | cur[i - W] | cur[i + W];
+                if (w > 0) nb |= cur[i - 1] >> 31;
+                if (w + 1 < W) nb |= cur[i + 1] << 31;
                 uint32_t s = v | (fr & nb), old;
                 do { old = s; s |= fr & ((s << 1) | (s >> 1)); } while (s != old);      // along c2 inside the word
-                if (s != v) { vis[i] = s; changed = 1; }
+                nxt[i] = s;
+                changed |= (s != v);
             }
         }
         if (!__syncthreads_or(changed)) break;
+        uint32_t* t = cur; cur = nxt; nxt = t;
     }
     // 1 - visible (voxelization.py:43), int32 [vs,vs,vs], coalesced along c2
     int32_t* out = voxels + (size_t)b * rows * vs;
     for (int i = tid; i < rows * vs; i += VOX_FILL_THREADS) {
         const int row = i / vs, c2 = i - row * vs;
-        out[i] = 1 - (int)((vis[row * W + (c2 >> 5)] >> (c2 & 31)) & 1u);
+        out[i] = 1 - (int)((cur[row * W + (c2 >> 5)] >> (c2 & 31)) & 1u);
     }
 }
 
