@@ -161,6 +161,9 @@ def reference_arm(args):
     if ref is None:
         if cpu is None:
             cpu = cpu_reference_arm(fv, ft, kw, args.steps, args.warmup)
+            line.update({'steps': args.steps, 'warmup': args.warmup})
+        else:
+            line.update({'steps': 2, 'warmup': 1})
         line.update({'value': cpu['value'], 'ms_per_step': cpu['ms_per_step'], 'gpu_launches': 0,
                      'config': {'workload': desc, 'per_gpu_batch': b, 'timed_on': 'host CPU cores: the reference CUDA kernels compiled for the host '
                                 '(oracle/_ref) -- no GPU or no baseline/_ref build available'},
@@ -229,8 +232,28 @@ def reference_arm(args):
     return line
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print to stdout (e.g. NCCL's version banner) to stderr, so that stdout carries exactly ONE
+    JSON line (emit())."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -238,7 +261,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        print(json.dumps(reference_arm(args)))
+        emit(reference_arm(args))
         return
 
     import numpy as np
@@ -409,7 +432,7 @@ def main():
                                                   'gendr.functional.render + backward', 'speedup_device_path': value / ref_val}
         except Exception as e:      # the extra must never break the contract line
             line['reference_cuda'] = {'unavailable': repr(e)[:200]}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
