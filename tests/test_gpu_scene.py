@@ -300,7 +300,7 @@ def test_camera_gradient_takes_the_torch_path():
         cam.set_eyes(eye)
         mesh = cam(pkg.Lighting()(pkg.Mesh(v, f, tex)))
         if pkg is gd:
-            assert mesh._pending_camera is None and mesh._pending_light is not None
+            assert mesh._pending_camera is None and mesh._pending_light is None      # both steps ran as torch ops
         img = pkg.GenDR(image_size=64, dist_func='logistic', dist_scale=0.03, dist_shape=0.0, dist_shift=0.0, aggr_alpha_t_conorm_p=0.0)(mesh)
         img.backward(g_img)
         grads[name] = eye.grad.cpu()
