@@ -6,10 +6,11 @@ container, camera transforms and lighting.  The rasterization forward/backward r
 """
 from . import functional
 from .lighting import AmbientLighting, DirectionalLighting, Lighting
+from .losses import FlattenLoss, LaplacianLoss
 from .mesh import Mesh
 from .renderer import GenDR
 from .transform import Look, LookAt, Projection
 
 __all__ = ['functional', 'AmbientLighting', 'DirectionalLighting', 'Lighting', 'Mesh', 'GenDR', 'Look', 'LookAt',
-           'Projection']
+           'Projection', 'LaplacianLoss', 'FlattenLoss']
 __version__ = '0.1.0'

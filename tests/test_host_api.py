@@ -115,3 +115,30 @@ def test_mesh_camera_lighting_pipeline_on_cpu():
     fv, ft, cfg = scenes.config_c1()
     want = torch.tensor([[0, 0.2693377435, 2], [-0.3110042512, -0.2693377435, 2], [0.3110042512, -0.2693377435, 2]])
     assert torch.allclose(fv[0, 0], want, atol=1e-6) and torch.allclose(ft, torch.full_like(ft, 0.5))
+
+
+def test_regularisers_match_the_reference_python():
+    """LaplacianLoss / FlattenLoss (gendr/losses.py) against the reference's own modules on a jittered icosphere, and their
+    defining properties (flat neighbourhoods cost nothing)."""
+    import scenes
+    from ref_gpu import load_reference
+    verts, faces = scenes.icosphere(2)
+    g = torch.Generator().manual_seed(0)
+    x = ((verts * 0.5)[None].repeat(3, 1, 1) + 0.02 * torch.randn(3, verts.shape[0], 3, generator=g)).requires_grad_(True)
+    lap, flat = gd.LaplacianLoss(verts, faces, average=True), gd.FlattenLoss(faces, average=False)
+    a, b = lap(x), flat(x)
+    assert a.ndim == 0 and b.shape == (3,) and float(a) > 0 and float(b.min()) > 0
+    (a + b.sum()).backward()
+    assert torch.isfinite(x.grad).all()
+    ref = load_reference()
+    if ref is not None:
+        ra, rb = ref.LaplacianLoss(verts, faces, average=True)(x), ref.FlattenLoss(faces, average=False)(x)
+        assert torch.allclose(a, ra, rtol=1e-5) and torch.allclose(b, rb, rtol=1e-4)
+    # a flat square split into two triangles: the shared edge is flat -> cos(dihedral) = -1 -> zero loss
+    quad = torch.tensor([[0., 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]])
+    loss = gd.FlattenLoss.__new__(gd.FlattenLoss)
+    torch.nn.Module.__init__(loss)
+    loss.nf, loss.average = 2, False
+    for name, idx in (('v0s', [0]), ('v1s', [2]), ('v2s', [1]), ('v3s', [3])):
+        loss.register_buffer(name, torch.tensor(idx))
+    assert float(loss(quad[None])) < 1e-4
