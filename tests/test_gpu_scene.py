@@ -289,13 +289,13 @@ def test_camera_gradient_takes_the_torch_path():
     import gendr_b200 as gd
     dev = _dev()
     ref = load_reference()
-    v, f, tex, _ = _scene_inputs(dev, B=2, sub=2, T=1)
-    g_img = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(9)).to(dev)
+    v, f, tex, _ = _scene_inputs(dev, B=3, sub=2, T=1)
+    g_img = torch.randn(3, 4, 64, 64, generator=torch.Generator().manual_seed(9)).to(dev)
     grads = {}
     for name, pkg in (('ours', gd), ('ref', ref)):
         if pkg is None:
             continue
-        eye = torch.tensor([[0.3, 0.8, -2.6], [1.2, 0.5, -2.3]], device=dev, requires_grad=True)
+        eye = torch.tensor([[0.3, 0.8, -2.6], [1.2, 0.5, -2.3], [-0.9, 0.2, -2.5]], device=dev, requires_grad=True)
         cam = pkg.LookAt(viewing_angle=15)
         cam.set_eyes(eye)
         mesh = cam(pkg.Lighting()(pkg.Mesh(v, f, tex)))
@@ -306,4 +306,6 @@ def test_camera_gradient_takes_the_torch_path():
         grads[name] = eye.grad.cpu()
     assert torch.isfinite(grads['ours']).all() and float(grads['ours'].abs().max()) > 0
     if 'ref' in grads:
-        assert _rel(grads['ours'], grads['ref']) <= 5e-2, _rel(grads['ours'], grads['ref'])
+        # all but the LAST batch item: its last face samples the texel behind the texture buffer in the reference (quirk Q3:
+        # undefined there, 0 here), which changes that item's colours and gradients
+        assert _rel(grads['ours'][:-1], grads['ref'][:-1]) <= 1e-3, _rel(grads['ours'][:-1], grads['ref'][:-1])
