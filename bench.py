@@ -82,7 +82,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits', '-lms', '100'],
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -90,18 +90,26 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(',')])
+
+    def window(self, t0, t1):
+        """restrict the statistics to samples that arrived inside the timed region [t0, t1] (perf_counter seconds)"""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        t0, t1 = getattr(self, 't0', None), getattr(self, 't1', None)
+        inside = [r[1:] for r in self.rows if t0 is not None and t0 <= r[0] <= t1 + 0.03]
+        rows = inside if inside else [r[1:] for r in self.rows]
+        sm = sorted(float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm),
+                'sampled': 'inside the timed region' if inside else 'around the timed region'}
 
 
 def cpu_reference_arm(fv, ft, kw, steps, warmup, sample_size=128):
@@ -191,11 +199,13 @@ def reference_arm(args):
     sampler = ClockSampler(0)
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w_begin = time.perf_counter()
     t0.record()
     for _ in range(steps):
         step()
     t1.record()
     torch.cuda.synchronize()
+    sampler.window(w_begin, time.perf_counter())
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1) / steps
     pairs = B * S * S * F
@@ -315,11 +325,13 @@ def main():
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    w_begin = time.perf_counter()
     t_begin.record()
     for i in range(args.steps):
         step(evs[i])
     t_end.record()
     torch.cuda.synchronize()
+    sampler.window(w_begin, time.perf_counter())
     if world > 1:
         dist.barrier()
     launches = lib.gendr_launch_count() - launches0
