@@ -289,13 +289,13 @@ def test_camera_gradient_takes_the_torch_path():
     import gendr_b200 as gd
     dev = _dev()
     ref = load_reference()
-    v, f, tex, _ = _scene_inputs(dev, B=3, sub=2, T=1)
-    g_img = torch.randn(3, 4, 64, 64, generator=torch.Generator().manual_seed(9)).to(dev)
+    v, f, tex, _ = _scene_inputs(dev, B=4, sub=2, T=1)       # not 3: the reference's torch.cross without `dim` (mesh.py:108) would pick the batch axis
+    g_img = torch.randn(4, 4, 64, 64, generator=torch.Generator().manual_seed(9)).to(dev)
     grads = {}
     for name, pkg in (('ours', gd), ('ref', ref)):
         if pkg is None:
             continue
-        eye = torch.tensor([[0.3, 0.8, -2.6], [1.2, 0.5, -2.3], [-0.9, 0.2, -2.5]], device=dev, requires_grad=True)
+        eye = torch.tensor([[0.3, 0.8, -2.6], [1.2, 0.5, -2.3], [-0.9, 0.2, -2.5], [0.0, 1.5, -2.2]], device=dev, requires_grad=True)
         cam = pkg.LookAt(viewing_angle=15)
         cam.set_eyes(eye)
         mesh = cam(pkg.Lighting()(pkg.Mesh(v, f, tex)))
