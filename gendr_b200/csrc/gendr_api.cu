@@ -789,8 +789,8 @@ int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, in
     uint32_t* scratch = smem ? nullptr : reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(workspace) + al256((size_t)batch * words * 4));
     GENDR_CUDA(cudaMemsetAsync(mask, 0, (size_t)batch * words * 4, st), "zero occupancy mask");
     if (num_faces > 0) {
-        const int ray_blocks = (vs * vs + 255) / 256;
-        voxel_surface_kernel<<<(unsigned)(batch * 3 * ray_blocks), 256, 0, st>>>(faces, mask, batch, num_faces, vs, W, ray_blocks);
+        const long long n = (long long)batch * num_faces * 3;
+        voxel_surface_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(faces, mask, batch, num_faces, vs, W);
         g_launches++;
         GENDR_CUDA(cudaGetLastError(), "voxel_surface_kernel launch");
     }

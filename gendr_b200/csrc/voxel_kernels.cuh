@@ -7,10 +7,10 @@
 // host synchronisations per flood-fill sweep until nothing changes (typically 30-60 sweeps).
 //
 // Here: TWO launches and no host synchronisation.
-//   voxel_surface_kernel  one CTA = 256 rays of one (batch item, axis); faces are staged through shared memory 256 at a time
-//                         as per-face constants (edge vectors, determinant), so the all-pairs ray x face loop reads them as
-//                         broadcast LDS.128; hits set bits in a packed occupancy mask (1 bit per voxel) with atomicOr.
-//                         Grid = B * 3 * ceil(vs^2 / 256) CTAs.
+//   voxel_surface_kernel  one thread = one (face, ray axis): instead of the reference's all-pairs ray x face loop the thread visits
+//                         only the lattice rays inside the face's bounding box (+2), which is certified per face not to drop
+//                         a ray the reference's fp32 test would accept (uncertifiable faces scan the whole lattice); hits set
+//                         bits in a packed occupancy mask (1 bit per voxel) with atomicOr.  Grid = ceil(3 B F / 128) CTAs.
 //   voxel_fill_kernel     one CTA per batch item: the whole volume lives in shared memory as bit masks (vs = 32: 3 x 4 KB);
 //                         vertex voxels are OR-ed in, the outside is flood-filled with word-parallel bit operations (32 voxels
 //                         per instruction, double-buffered sweeps until one changes nothing, __syncthreads_or), and the int32
@@ -28,75 +28,95 @@
 
 namespace gendr {
 
-constexpr int VOX_CHUNK = 256;          // faces staged per shared-memory chunk
 constexpr int VOX_FILL_THREADS = 1024;
 
 // word index of voxel (c0, c1, c2) in the packed mask of one batch item: [c0][c1][W] words, bit = c2 & 31
 __device__ __forceinline__ int vox_word(int c0, int c1, int c2, int vs, int W) { return (c0 * vs + c1) * W + (c2 >> 5); }
 
-__global__ void __launch_bounds__(256) voxel_surface_kernel(const float* __restrict__ faces, uint32_t* __restrict__ mask, int B, int F,
-                                                            int vs, int W, int ray_blocks) {
-    __shared__ float4 fc[VOX_CHUNK][3];     // per face: (f0 f1 f2 y1d) (x1d z1d y2d x2d) (z2d det sdet -)
-    const int tid = threadIdx.x;
-    int blk = blockIdx.x;
-    const int rb = blk % ray_blocks; blk /= ray_blocks;
-    const int axis = blk % 3;
-    const int b = blk / 3;
-    // voxelization.py:14-19: dim 0 -> faces[..., [2,1,0]], dim 1 -> faces[..., [0,2,1]], dim 2 -> as is; results transposed back
-    const int yr = (axis == 0) ? 2 : 0, xr = (axis == 2) ? 1 : ((axis == 0) ? 1 : 2), zr = (axis == 0) ? 0 : ((axis == 1) ? 1 : 2);
-    const int ray = rb * 256 + tid;
-    const bool active = ray < vs * vs;
-    const int y = ray % vs, x = (ray / vs) % vs;                 // :50-51
-    const float yf = (float)y, xf = (float)x, fvs = (float)vs;
-    uint32_t* m = mask + (size_t)b * vs * vs * W;
+// select component k (0..2) of a vertex without dynamic register indexing
+__device__ __forceinline__ float pick3(float a, float b, float c, int k) { return k == 0 ? a : (k == 1 ? b : c); }
 
-    for (int f0 = 0; f0 < F; f0 += VOX_CHUNK) {
-        const int nf = min(VOX_CHUNK, F - f0);
-        __syncthreads();
-        if (tid < nf) {
-            const float* f = faces + ((size_t)b * F + f0 + tid) * 9;
-            float v[9];
+// One thread = one (face, ray axis).  The reference tests every lattice ray against every face (sub1, :36-93); a ray outside the
+// face's bounding box cannot pass its test, so the thread only visits the lattice points of the box grown by two units per side.
+// That this never drops a ray the REFERENCE would accept is certified per face (else the whole lattice is scanned):
+//   * for a point at least one unit outside the box some barycentric coordinate is <= -1/(3w) in exact arithmetic
+//     (p = sum b_i v_i with sum b_i = 1: x_p >= xmax + 1 forces sum of the negative b_i <= -1/w; w = box extent);
+//   * the reference's fp32 numerators carry an absolute error <= 12 eps w M (M = largest |coordinate| incl. the lattice size),
+//     its quotients therefore <= ~20 eps w M / |det|, which stays below 1/(12 w) when |det| >= 7e-5 w^2 M  (4x margin);
+//   * vertex coordinates must be finite and |det| normal.
+// Faces failing the certificate (slivers with aspect below ~1e-3, faces seen edge-on along this axis, NaN/inf, huge
+// coordinates) visit all vs^2 rays -- cooperatively, 32 rays per step of their warp.
+struct VoxFace { float f0, f1, f2, y1d, x1d, z1d, y2d, x2d, z2d, det; int axis, b; };
+
+// the reference's ray / face test (sub1, :56-92) for lattice ray (y, x) of the face's (yr, xr) plane; sets the four voxels
+__device__ __forceinline__ void vox_test_ray(const VoxFace& t, int y, int x, int vs, int W, uint32_t* __restrict__ mask) {
+    const float ypd = __fsub_rn((float)y, t.f0), xpd = __fsub_rn((float)x, t.f1);     // :63-64
+    const float t1 = __fdiv_rn(__fmaf_rn(t.y2d, xpd, -__fmul_rn(t.x2d, ypd)), t.det); // :67
+    const float t2 = __fdiv_rn(__fmaf_rn(t.x1d, ypd, -__fmul_rn(t.y1d, xpd)), t.det); // :68
+    if (t1 < 0.f) return;
+    if (t2 < 0.f) return;
+    if (1.f < __fadd_rn(t1, t2)) return;                                              // :71
+    const int zi = __float2int_rd(__fadd_rn(t.f2, __fmaf_rn(t.z1d, t1, __fmul_rn(t.z2d, t2))));   // :72
+    if (zi < 0 || zi >= vs) return;
+    // voxelization.py:14-19: dim 0 -> faces[..., [2,1,0]], dim 1 -> faces[..., [0,2,1]], dim 2 -> as is; results transposed back
+    const int yr = (t.axis == 0) ? 2 : 0, xr = (t.axis == 2) ? 1 : ((t.axis == 0) ? 1 : 2);
+    uint32_t* m = mask + (size_t)t.b * vs * vs * W;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = __fmul_rn(__ldg(f + k), fvs);          // voxelization.py:50  faces *= size
-            const float a0 = v[yr], a1 = v[xr], a2 = v[zr];
-            const float y1d = __fsub_rn(v[3 + yr], a0), x1d = __fsub_rn(v[3 + xr], a1), z1d = __fsub_rn(v[3 + zr], a2);
-            const float y2d = __fsub_rn(v[6 + yr], a0), x2d = __fsub_rn(v[6 + xr], a1), z2d = __fsub_rn(v[6 + zr], a2);
-            const float det = __fmaf_rn(x1d, y2d, -__fmul_rn(y1d, x2d));
-            // sign of det for the exact-safe early rejection below; 0 disables it (|det| outside [2^-60, 2^60], 0 or NaN)
-            const float ad = fabsf(det);
-            const float sdet = (ad > 8.6736174e-19f && ad < 1.1529215e18f) ? copysignf(1.f, det) : 0.f;
-            fc[tid][0] = make_float4(a0, a1, a2, y1d);
-            fc[tid][1] = make_float4(x1d, z1d, y2d, x2d);
-            fc[tid][2] = make_float4(z2d, det, sdet, 0.f);
-        }
-        __syncthreads();
-        if (!active) continue;
-        for (int j = 0; j < nf; ++j) {
-            const float4 A = fc[j][0], Bq = fc[j][1], Cq = fc[j][2];
-            const float det = Cq.y;
-            if (det == 0.f) continue;                                                    // :66
-            const float ypd = __fsub_rn(yf, A.x), xpd = __fsub_rn(xf, A.y);              // :63-64
-            const float n1 = __fmaf_rn(Bq.z, xpd, -__fmul_rn(Bq.w, ypd));                // y2d*xpd - x2d*ypd
-            // Early rejection, exact: with |det| <= 2^60 a numerator of the wrong sign and magnitude > 1e-20 gives a quotient
-            // that is negative and non-zero (>= 8e-39 in magnitude), i.e. `t < 0` in the reference (:69-70).
-            if (n1 * Cq.z < -1e-20f) continue;
-            const float n2 = __fmaf_rn(Bq.x, ypd, -__fmul_rn(A.w, xpd));                 // -y1d*xpd + x1d*ypd
-            if (n2 * Cq.z < -1e-20f) continue;
-            const float t1 = __fdiv_rn(n1, det), t2 = __fdiv_rn(n2, det);                // :67-68
-            if (t1 < 0.f) continue;
-            if (t2 < 0.f) continue;
-            if (1.f < __fadd_rn(t1, t2)) continue;                                       // :71
-            const int zi = __float2int_rd(__fadd_rn(A.z, __fmaf_rn(Bq.y, t1, __fmul_rn(Cq.x, t2))));   // :72
-            if (zi < 0 || zi >= vs) continue;
+    for (int k = 0; k < 4; ++k) {                                                     // :73-92: the four voxels around the ray
+        const int yi = y - (k & 1), xi = x - (k >> 1);
+        if (yi < 0 || xi < 0) continue;
+        // (yi, xi, zi) play the roles (yr, xr, zr) of the final [c0][c1][c2] grid
+        const int c0 = (yr == 0) ? yi : ((xr == 0) ? xi : zi), c1 = (yr == 1) ? yi : ((xr == 1) ? xi : zi),
+                  c2 = (yr == 2) ? yi : ((xr == 2) ? xi : zi);
+        atomicOr(m + vox_word(c0, c1, c2, vs, W), 1u << (c2 & 31));
+    }
+}
+
+__global__ void __launch_bounds__(128) voxel_surface_kernel(const float* __restrict__ faces, uint32_t* __restrict__ mask, int B, int F,
+                                                            int vs, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in_range = i < (long long)B * F * 3;
+    const long long bf = in_range ? i / 3 : 0;
+    VoxFace t;
+    t.axis = (int)(i % 3);
+    t.b = (int)(bf / F);
+    const int yr = (t.axis == 0) ? 2 : 0, xr = (t.axis == 2) ? 1 : ((t.axis == 0) ? 1 : 2), zr = (t.axis == 0) ? 0 : ((t.axis == 1) ? 1 : 2);
+    const float fvs = (float)vs;
+    const float* f = faces + bf * 9;
+    float v[9];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                                                // :73-92: the four voxels around the ray
-                const int yi = y - (q & 1), xi = x - (q >> 1);
-                if (yi < 0 || xi < 0) continue;
-                int c[3];
-                c[yr] = yi; c[xr] = xi; c[zr] = zi;
-                atomicOr(m + vox_word(c[0], c[1], c[2], vs, W), 1u << (c[2] & 31));
-            }
-        }
+    for (int k = 0; k < 9; ++k) v[k] = in_range ? __fmul_rn(__ldg(f + k), fvs) : 0.f;  // voxelization.py:50  faces *= size
+    t.f0 = pick3(v[0], v[1], v[2], yr); t.f1 = pick3(v[0], v[1], v[2], xr); t.f2 = pick3(v[0], v[1], v[2], zr);
+    const float g0 = pick3(v[3], v[4], v[5], yr), g1 = pick3(v[3], v[4], v[5], xr), h0 = pick3(v[6], v[7], v[8], yr),
+                h1 = pick3(v[6], v[7], v[8], xr);
+    t.y1d = __fsub_rn(g0, t.f0); t.x1d = __fsub_rn(g1, t.f1); t.z1d = __fsub_rn(pick3(v[3], v[4], v[5], zr), t.f2);
+    t.y2d = __fsub_rn(h0, t.f0); t.x2d = __fsub_rn(h1, t.f1); t.z2d = __fsub_rn(pick3(v[6], v[7], v[8], zr), t.f2);
+    t.det = __fmaf_rn(t.x1d, t.y2d, -__fmul_rn(t.y1d, t.x2d));
+    const bool live = in_range && !(t.det == 0.f);                                    // :66 skips the face for every ray
+    // lattice range to visit (see the certificate above)
+    const float ylo = fminf(fminf(t.f0, g0), h0), yhi = fmaxf(fmaxf(t.f0, g0), h0), xlo = fminf(fminf(t.f1, g1), h1), xhi = fmaxf(fmaxf(t.f1, g1), h1);
+    const float w = fmaxf(yhi - ylo, xhi - xlo);
+    const float M = fmaxf(fmaxf(fmaxf(fabsf(ylo), fabsf(yhi)), fmaxf(fabsf(xlo), fabsf(xhi))), fvs);
+    const float ad = fabsf(t.det);
+    const bool certified = (M < 1e6f) && (ad >= 7e-5f * w * w * M) && (ad > 1e-30f) && (ad < 1e30f);   // false for NaN / inf
+    if (live && certified) {
+        const int y0 = max(0, (int)floorf(ylo) - 1), y1 = min(vs - 1, (int)ceilf(yhi) + 1);
+        const int x0 = max(0, (int)floorf(xlo) - 1), x1 = min(vs - 1, (int)ceilf(xhi) + 1);
+        for (int x = x0; x <= x1; ++x)
+            for (int y = y0; y <= y1; ++y) vox_test_ray(t, y, x, vs, W, mask);
+    }
+    // faces without a certificate: the whole warp scans the full lattice for each of them (32 rays per step)
+    unsigned todo = __ballot_sync(0xffffffffu, live && !certified);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        VoxFace u;
+        u.f0 = __shfl_sync(0xffffffffu, t.f0, src); u.f1 = __shfl_sync(0xffffffffu, t.f1, src); u.f2 = __shfl_sync(0xffffffffu, t.f2, src);
+        u.y1d = __shfl_sync(0xffffffffu, t.y1d, src); u.x1d = __shfl_sync(0xffffffffu, t.x1d, src); u.z1d = __shfl_sync(0xffffffffu, t.z1d, src);
+        u.y2d = __shfl_sync(0xffffffffu, t.y2d, src); u.x2d = __shfl_sync(0xffffffffu, t.x2d, src); u.z2d = __shfl_sync(0xffffffffu, t.z2d, src);
+        u.det = __shfl_sync(0xffffffffu, t.det, src); u.axis = __shfl_sync(0xffffffffu, t.axis, src); u.b = __shfl_sync(0xffffffffu, t.b, src);
+        for (int r = lane; r < vs * vs; r += 32) vox_test_ray(u, r % vs, r / vs, vs, W, mask);
     }
 }
 

@@ -94,3 +94,40 @@ def test_voxelizer_vs_reference_cuda_and_mesh_api():
         want = ref.Mesh(v, f).voxelize(size)
         got = gd.Mesh(v, f).voxelize(size)
         assert got.dtype == want.dtype and torch.equal(got, want), 'size %d: differs in %d voxels' % (size, int((got != want).sum()))
+
+
+@pytest.mark.parametrize('size', [16, 32, 50])
+def test_voxelizer_box_culling_is_exact_on_hard_faces(size):
+    """The surface kernel visits only the lattice rays inside each face's (certified) bounding box, the oracle tests every ray
+    against every face like the reference: slivers down to aspect 1e-7, faces larger than the cube, tiny faces, faces on exact
+    lattice planes and partly outside must all give the bit-identical grid."""
+    from oracle.voxel_oracle import VoxelOracle
+    dev = _dev()
+    rng = np.random.default_rng(size)
+    faces = []
+    for k in range(240):
+        c = rng.random(3) * 1.2 - 0.1
+        kind = k % 6
+        if kind == 0:       # ordinary
+            tri = c + (rng.random((3, 3)) - 0.5) * 0.3
+        elif kind == 1:     # sliver: third vertex almost on the line through the first two
+            a, d = c, (rng.random(3) - 0.5) * 0.6
+            tri = np.stack([a, a + d, a + d * rng.random() + (rng.random(3) - 0.5) * 10.0 ** rng.uniform(-7, -2)])
+        elif kind == 2:     # larger than the cube
+            tri = c + (rng.random((3, 3)) - 0.5) * 4.0
+        elif kind == 3:     # tiny
+            tri = c + (rng.random((3, 3)) - 0.5) * 10.0 ** rng.uniform(-5, -2)
+        elif kind == 4:     # vertices on exact lattice positions
+            tri = rng.integers(0, size + 1, (3, 3)) / size
+        else:               # far outside with one vertex inside
+            tri = np.stack([c, c + (rng.random(3) - 0.5) * 50, c + (rng.random(3) - 0.5) * 50])
+        faces.append(tri)
+    inp = np.asarray(faces, np.float32).reshape(2, 120, 3, 3)
+    oracle = VoxelOracle('port')
+    oracle.set_mode(1)
+    try:
+        want = oracle.voxelize(inp, size)
+    finally:
+        oracle.set_mode(0)
+    got = _ours(inp, size, dev)
+    assert np.array_equal(got, want), 'differs in %d voxels' % int((got != want).sum())
