@@ -142,3 +142,54 @@ def test_regularisers_match_the_reference_python():
     for name, idx in (('v0s', [0]), ('v1s', [2]), ('v2s', [1]), ('v3s', [3])):
         loss.register_buffer(name, torch.tensor(idx))
     assert float(loss(quad[None])) < 1e-4
+
+
+def test_binding_table_matches_header_signatures():
+    """Every entry of gendr_b200._lib.SIGNATURES has the argument count and the argument kinds (pointer / int / float / size_t) of
+    the C declaration in include/gendr_b200.h -- a mismatch would corrupt the call stack silently under ctypes."""
+    text = open(os.path.join(ROOT, 'include', 'gendr_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = dict(re.findall(r'\b(gendr_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;', text, flags=re.S))
+    assert sorted(decls) == sorted(_lib.SIGNATURES)
+
+    def kind_of_c(arg):
+        arg = ' '.join(arg.split())
+        if arg in ('void', ''):
+            return None
+        if '*' in arg:
+            return 'ptr'
+        base = arg.rsplit(' ', 1)[0] if ' ' in arg else arg
+        return {'int': 'int', 'float': 'float', 'size_t': 'size_t', 'long long': 'longlong'}[base.replace('const ', '')]
+
+    def kind_of_py(t):
+        if t in (C.c_void_p,) or hasattr(t, 'contents') or t is C.c_char_p:
+            return 'ptr'
+        return {C.c_int: 'int', C.c_float: 'float', C.c_size_t: 'size_t', C.c_longlong: 'longlong'}[t]
+
+    for name, args in decls.items():
+        c_kinds = [k for k in (kind_of_c(a) for a in args.split(',')) if k is not None]
+        py_kinds = [kind_of_py(t) for t in _lib.SIGNATURES[name][1]]
+        assert c_kinds == py_kinds, (name, c_kinds, py_kinds)
+    for cls, cname in ((_lib.CameraParams, 'gendr_camera_params'), (_lib.LightParams, 'gendr_light_params')):
+        body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, flags=re.S).group(1)
+        fields = [(t, n) for t, n in re.findall(r'\b(int|float)\s+([a-z_]+)(?:\[3\])?;', body)]
+        py = [(('int' if f[1] is C.c_int else 'float'), f[0]) for f in cls._fields_]
+        assert fields == py, (cname, fields, py)
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` without a GPU falls back to the CPU shim of the reference kernels and still prints exactly one
+    JSON line with the keys of the contract."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', '--workload', 'c2'],
+                       capture_output=True, text=True, timeout=600)
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert r.returncode == 0 and len(lines) == 1, (r.returncode, r.stdout[-500:], r.stderr[-500:])
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'dtype', 'data',
+                'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and 'workload' in d['config']
