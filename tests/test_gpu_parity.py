@@ -343,36 +343,89 @@ def test_reference_cuda_c2_full(reference_cuda):
     _vs_reference(reference_cuda, 'C2', fv, ft, dev, double_side=False, **cfg)
 
 
-def test_reference_cuda_c3_slice(reference_cuda):
+def test_reference_cuda_c3_full_batch(reference_cuda):
+    """C3 exactly as BASELINE.json states it: 8192 faces, 256x256, gaussian + einstein, B = 64 (the headline workload)."""
     dev = _dev()
-    fv, ft, cfg = scenes.config_c3(batch=4)
+    fv, ft, cfg = scenes.config_c3(batch=64)
     fv, ft = scenes.with_sentinel(fv, ft)
-    _vs_reference(reference_cuda, 'C3', fv, ft, dev, double_side=False, **cfg)
+    _vs_reference(reference_cuda, 'C3/B64', fv, ft, dev, double_side=False, **cfg)
 
 
-def test_reference_cuda_c4_slice(reference_cuda):
+def test_reference_cuda_c4_b8(reference_cuda):
+    """C4 (dense: cauchy + yager p=2, nothing cullable) at B = 8 -- one eighth of a GPU's 64-view share of the 512-view job."""
     dev = _dev()
-    fv, ft, cfg = scenes.config_c4(batch=1)
+    fv, ft, cfg = scenes.config_c4(batch=8)
     fv, ft = scenes.with_sentinel(fv, ft)
-    _vs_reference(reference_cuda, 'C4', fv, ft, dev, double_side=False, **cfg)
+    _vs_reference(reference_cuda, 'C4/B8', fv, ft, dev, double_side=False, **cfg)
+
+
+@pytest.fixture(scope='module')
+def c5_mesh():
+    fv, ft, _ = scenes.config_c3(batch=1)            # 8192 faces (n = 64), the C3 mesh
+    return scenes.with_sentinel(fv, ft)
 
 
 @pytest.mark.parametrize('dist,dkw', scenes.DIST_SWEEP, ids=[d for d, _ in scenes.DIST_SWEEP])
-def test_reference_cuda_c5_sweep(reference_cuda, dist, dkw):
-    """C5: every distribution x every t-conorm (18 x 10) on the C3 mesh, 128x128, both RGB modes on a subset."""
+def test_reference_cuda_c5_sweep(reference_cuda, c5_mesh, dist, dkw):
+    """C5 at the stated size: every distribution x every t-conorm (18 x 10) on the 8192-face mesh at 256x256, fwd + bwd against
+    the reference's CUDA kernels within 1e-4, plus hard RGB (double-sided) for every distribution.  Strict for every case --
+    including gumbel_min / gamma_rev / levy_rev / wigner+max, which the CPU-oracle tests above can only check in part."""
     dev = _dev()
-    fv, ft, _ = scenes.config_c3(batch=1, n=32)
-    fv, ft = scenes.with_sentinel(fv, ft)
+    fv, ft = c5_mesh
     failures = []
     cases = [dict(aggr_alpha_func=t, aggr_alpha_t_conorm_p=p, double_side=False) for t, p in scenes.TCN_SWEEP]
     cases.append(dict(aggr_alpha_func='probabilistic', aggr_rgb_func='hard', double_side=True))
     for case in cases:
-        kw = dict(image_size=128, dist_func=dist, **case, **dkw)
+        kw = dict(image_size=256, dist_func=dist, **case, **dkw)
         try:
             _vs_reference(reference_cuda, 'C5/%s/%s/%s' % (dist, case['aggr_alpha_func'], case.get('aggr_rgb_func', 'softmax')), fv, ft, dev, **kw)
         except AssertionError as e:
             failures.append(str(e).splitlines()[0])
     assert not failures, '\n'.join(failures)
+
+
+AXES_COMBOS = [('logistic', {}, 'probabilistic', None), ('gaussian', {}, 'einstein', None), ('cauchy', {}, 'yager', 2.0),
+               ('uniform', {}, 'max', None), ('gamma', dict(dist_shape=2.0), 'hamacher', 0.5)]
+
+
+@pytest.mark.parametrize('dist,dkw,tcn,tp', AXES_COMBOS, ids=['%s-%s' % (c[0], c[2]) for c in AXES_COMBOS])
+def test_reference_cuda_axes_full_size(reference_cuda, c5_mesh, dist, dkw, tcn, tp):
+    """The axes the C5 sweep does not vary, against the reference's CUDA kernels on the 8192-face mesh at 256x256:
+    dist_squared, texture_type='vertex', texture_res 2 and 3 (T = 4, 9), double_side both ways, hard RGB with textures."""
+    dev = _dev()
+    fv, _ = c5_mesh
+    gen = torch.Generator().manual_seed(11)
+    F = fv.shape[1]
+    tex = {1: torch.rand(1, F, 1, 3, generator=gen), 4: torch.rand(1, F, 4, 3, generator=gen), 9: torch.rand(1, F, 9, 3, generator=gen),
+           'v': torch.rand(1, F, 3, 3, generator=gen)}
+    base = dict(image_size=256, dist_func=dist, aggr_alpha_func=tcn, aggr_alpha_t_conorm_p=tp, **dkw)
+    variants = [
+        ('squared', tex[1], dict(dist_squared=True, dist_scale=1e-4, double_side=False)),
+        ('squared/double_side', tex[1], dict(dist_squared=True, dist_scale=1e-4, double_side=True)),
+        ('vertex', tex['v'], dict(texture_type='vertex', double_side=False)),
+        ('vertex/double_side/hard_rgb', tex['v'], dict(texture_type='vertex', double_side=True, aggr_rgb_func='hard')),
+        ('res2', tex[4], dict(double_side=False)),
+        ('res2/double_side', tex[4], dict(double_side=True)),
+        ('res3', tex[9], dict(double_side=True)),
+        ('res3/hard_rgb', tex[9], dict(double_side=False, aggr_rgb_func='hard')),
+        ('double_side', tex[1], dict(double_side=True)),
+    ]
+    failures = []
+    for name, ft, extra in variants:
+        try:
+            _vs_reference(reference_cuda, 'axes/%s/%s/%s' % (dist, tcn, name), fv, ft, dev, **dict(base, **extra))
+        except AssertionError as e:
+            failures.append(str(e).splitlines()[0])
+    assert not failures, '\n'.join(failures)
+
+
+def test_reference_cuda_c2_scaled_views(reference_cuda):
+    """C2 mesh with the paper-tuned scale of logistic + probabilistic (10^-2.0 is the default; 10^-1.5 widens every face's
+    footprint ~3x) and anti-aliasing through the module API -- the configuration experiments/opt_shape.py runs."""
+    dev = _dev()
+    fv, ft, cfg = scenes.config_c2(batch=4)
+    fv, ft = scenes.with_sentinel(fv, ft)
+    _vs_reference(reference_cuda, 'C2/tau=10^-1.5', fv, ft, dev, double_side=False, **dict(cfg, dist_scale=10 ** -1.5))
 
 
 # ---- size-independent properties at the headline size ----------------------------------------------------------
