@@ -67,6 +67,7 @@ SIGNATURES = {
     'gendr_launch_count': (C.c_longlong, []),
     'gendr_probe_pairs': (_I, [_P, _P, _P, _I, _P]),
     'gendr_selftest_division': (C.c_longlong, [C.c_longlong]),
+    'gendr_selftest_scalar_device': (_F, [_I, _I, _F, _F, _F, _F, _F, _F]),
 }
 
 _lib = None

@@ -186,36 +186,54 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     return 0;
 }
 
-// ---- scalar functions: one device thread, same templates as the render kernels --------------------------------
+// ---- scalar functions (K.cpp:195-236 -> K.cu:1230-1270): evaluated ON THE HOST by the host instantiation of the very templates
+// the render kernels use (they are __host__ __device__, exactly like the reference's sigmoid_*_cuda / t_conorm_*_cuda) -- no
+// device, no allocation, no launch.  scalar_kernel runs the same switch in one device thread; it exists for the self-test
+// gendr_selftest_scalar_device (host and device instantiations must agree).
 template <int D> struct DistEval {
-    static __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P, const Consts& K) {
+    static __host__ __device__ float run(int id, bool pdf, float s, float x, const RenderParams& P, const Consts& K) {
+#ifdef __CUDA_ARCH__
         if (id == D) return pdf ? dist_pdf<D>(s, x, P, K) : (P.aggr_alpha_func == T_MAX ? dist_cdf<D, true, false>(s, x, P, K) : dist_cdf<D, false, false>(s, x, P, K));
+#else   // host: always the reference's own mixed fp32/fp64 expressions (the fp32 re-formulations rely on a fused multiply-add)
+        if (id == D) return pdf ? dist_pdf<D>(s, x, P, K) : dist_cdf<D, true, false>(s, x, P, K);
+#endif
         return DistEval<D + 1>::run(id, pdf, s, x, P, K);
     }
 };
 template <> struct DistEval<D_COUNT> {
-    static __device__ float run(int, bool, float, float, const RenderParams&, const Consts&) { return CUDART_NAN_F; }
+    static __host__ __device__ float run(int, bool, float, float, const RenderParams&, const Consts&) { return gd_nan(); }
 };
-__global__ void scalar_kernel(const __grid_constant__ RenderParams P, int what, int id, float a, float b, float* out) {
-    float r;
+static __host__ __device__ float eval_scalar(const RenderParams& P, int what, int id, float a, float b) {
     const Consts K = make_consts(P);
-    if (what == 0) r = DistEval<0>::run(id, false, a, b, P, K);
-    else if (what == 1) r = DistEval<0>::run(id, true, a, b, P, K);
-    else if (what == 2) r = (id >= T_HAMACHER) ? tconorm_fold<true>(id, a, b, P) : tconorm_fold<false>(id, a, b, P);
-    else r = (id >= T_HAMACHER) ? tconorm_dS<true>(id, a, b, P) : tconorm_dS<false>(id, a, b, P);
-    *out = r;
+    if (what == 0) return DistEval<0>::run(id, false, a, b, P, K);
+    if (what == 1) return DistEval<0>::run(id, true, a, b, P, K);
+    if (what == 2) return (id >= T_HAMACHER) ? tconorm_fold<true>(id, a, b, P) : tconorm_fold<false>(id, a, b, P);
+    return (id >= T_HAMACHER) ? tconorm_dS<true>(id, a, b, P) : tconorm_dS<false>(id, a, b, P);
+}
+__global__ void scalar_kernel(const __grid_constant__ RenderParams P, int what, int id, float a, float b, float* out) {
+    *out = eval_scalar(P, what, id, a, b);
 }
 
-static float run_scalar(int what, int id, float a, float b, float scale, float shape, float shift, float p) {
+static bool scalar_params(RenderParams& P, int what, int id, float scale, float shape, float shift, float p) {
     gendr_render_params u;
     memset(&u, 0, sizeof u);
     u.image_size = 1; u.dist_func = (what < 2 && id >= 0 && id < D_COUNT) ? id : 0; u.dist_scale = scale; u.dist_shape = shape;
     u.dist_shift = shift; u.dist_eps = 1.f; u.aggr_alpha_func = (what >= 2 && id >= 0 && id < T_COUNT) ? id : 0;
-    u.aggr_alpha_t_conorm_p = p; u.aggr_rgb_gamma = 1.f;
+    u.aggr_alpha_t_conorm_p = p; u.aggr_rgb_func = 1; u.aggr_rgb_gamma = 1.f;
+    if (make_params(P, 1, 1, 1, &u) != 0) return false;
+    return !((what < 2 && (id < 0 || id >= D_COUNT)) || (what >= 2 && (id < 1 || id >= T_COUNT)));
+}
+
+static float run_scalar(int what, int id, float a, float b, float scale, float shape, float shift, float p) {
+    RenderParams P;
+    if (!scalar_params(P, what, id, scale, shape, shift, p)) return std::numeric_limits<float>::quiet_NaN();
+    return eval_scalar(P, what, id, a, b);
+}
+
+static float run_scalar_device(int what, int id, float a, float b, float scale, float shape, float shift, float p) {
     RenderParams P;
     const float nan = std::numeric_limits<float>::quiet_NaN();
-    if (make_params(P, 1, 1, 1, &u) != 0) return nan;
-    if ((what < 2 && (id < 0 || id >= D_COUNT)) || (what >= 2 && (id < 1 || id >= T_COUNT))) return nan;
+    if (!scalar_params(P, what, id, scale, shape, shift, p)) return nan;
     float* d = nullptr;
     if (cudaMalloc(&d, sizeof(float)) != cudaSuccess) { fail((int)cudaGetLastError(), "scalar cudaMalloc"); return nan; }
     scalar_kernel<<<1, 1>>>(P, what, id, a, b, d);
@@ -816,6 +834,10 @@ float gendr_t_conorm_forward(int id, float a_existing, float b_new, int face_id,
 float gendr_t_conorm_backward(int id, float a_all, float b_current, int number_of_faces, float p) {
     (void)number_of_faces;
     return run_scalar(3, id, a_all, b_current, 1.f, 0.f, 0.f, p);
+}
+
+float gendr_selftest_scalar_device(int what, int id, float a, float b, float scale, float shape, float shift, float p) {
+    return run_scalar_device(what, id, a, b, scale, shape, shift, p);
 }
 
 long long gendr_selftest_division(long long n) {

@@ -175,7 +175,9 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
                                        float* h_soft_colors, float* h_grad_faces, float* h_grad_textures,
                                        int batch, int num_faces, int texture_size, const gendr_render_params* params);
 
-/* Scalar functions of the reference module (evaluated by the same device code the kernels use). */
+/* Scalar functions of the reference module.  Like the reference's (host instantiations of __host__ __device__ templates,
+ * K.cu:1230-1270) they run on the CPU: no device, no launch, no allocation -- animations/distributions_to_csv.py:19 calls them
+ * thousands of times.  They are the host instantiation of the same templates the render kernels use. */
 float gendr_sigmoid_forward(int function_id, float sign, float x, float scale, float dist_shape, float dist_shift);
 float gendr_sigmoid_backward(int function_id, float sign, float x, float scale, float dist_shape, float dist_shift);
 float gendr_t_conorm_forward(int t_conorm_id, float a_existing, float b_new, int face_id, float t_conorm_p);
@@ -186,6 +188,9 @@ const char* gendr_last_error(void);
 const char* gendr_version(void);
 /* number of kernels this library has launched since load (bench.py's "gpu_launches") */
 long long gendr_launch_count(void);
+/* self-test: the device instantiation of a scalar function, evaluated by ONE GPU thread (what: 0 sigmoid_forward, 1 sigmoid_backward,
+ * 2 t_conorm_forward, 3 t_conorm_backward; a, b = (sign, x) or (a, b)); tests compare it with the host functions above */
+float gendr_selftest_scalar_device(int what, int id, float a, float b, float scale, float shape, float shift, float p);
 /* self-test: number of (dividend, divisor) pairs out of n pseudo-random ones for which the library's shared-reciprocal
  * division differs from IEEE division by a single bit (must be 0); -1 on CUDA error */
 long long gendr_selftest_division(long long n);

@@ -82,23 +82,35 @@ def reference_cuda():
     return ref
 
 
-# ---- scalar functions (K.cpp:233-236) vs oracle -----------------------------------------------------------------
+# ---- scalar functions (K.cpp:233-236): DEVICE instantiation vs oracle, and host == device --------------------------
+# The module's sigmoid_* / t_conorm_* run on the host (tests/test_scalar_host_cpu.py checks them without a GPU); the kernels use
+# the device instantiation of the same templates, evaluated here by one GPU thread through gendr_selftest_scalar_device.
+def _dev_scalar(what, fid, a, b, scale=1.0, shape=0.0, shift=0.0, p=0.0):
+    from gendr_b200 import _lib
+    return float(_lib.load().gendr_selftest_scalar_device(what, fid, a, b, scale, shape, shift, p))
+
+
 def test_scalar_distributions(gpu_oracle):
     port_oracle = gpu_oracle
     _dev()
     from gendr_b200.cuda import generalized_renderer as ext
-    worst = 0.0
     for did in range(18):
         shape = 2.0 if did in (14, 15) else 0.0
         for sign in (-1.0, 1.0):
             for x in (0.0, 1e-3, 0.01, 0.05, 0.1, 0.3, 0.7, 1.0, 1.3, 2.0):
                 for shift in ((0.0,) if did < 12 else (0.0, 0.5)):
                     e = port_oracle.sigmoid_forward(did, sign, x * 0.1, 0.1, shape, shift)
-                    g = ext.sigmoid_forward(did, sign, x * 0.1, 0.1, shape, shift)
+                    g = _dev_scalar(0, did, sign, x * 0.1, 0.1, shape, shift)
                     assert (math.isnan(e) and math.isnan(g)) or abs(g - e) <= 2e-6 + 2e-5 * abs(e), ('cdf', did, sign, x, shift, g, e)
+                    h = ext.sigmoid_forward(did, sign, x * 0.1, 0.1, shape, shift)      # host instantiation
+                    if not (did == 3 and x == 1.0):    # wigner at x == tau: tau^2 - x^2 is +-1 ulp of cancellation, fused on the GPU only
+                        assert (math.isnan(h) and math.isnan(g)) or abs(g - h) <= 2e-6 + 2e-5 * abs(h), ('cdf host/device', did, sign, x, shift, g, h)
                     e = port_oracle.sigmoid_backward(did, sign, x * 0.1, 0.1, shape, shift)
-                    g = ext.sigmoid_backward(did, sign, x * 0.1, 0.1, shape, shift)
+                    g = _dev_scalar(1, did, sign, x * 0.1, 0.1, shape, shift)
                     assert (math.isnan(e) and math.isnan(g)) or abs(g - e) <= 1e-5 * max(1.0, abs(e)) + 2e-5 * abs(e), ('pdf', did, sign, x, shift, g, e)
+                    h = ext.sigmoid_backward(did, sign, x * 0.1, 0.1, shape, shift)
+                    if not (did == 3 and x == 1.0):
+                        assert (math.isnan(h) and math.isnan(g)) or abs(g - h) <= 1e-5 * max(1.0, abs(h)) + 2e-5 * abs(h), ('pdf host/device', did, sign, x, shift, g, h)
 
 
 def test_scalar_t_conorms(port_oracle):
@@ -109,24 +121,23 @@ def test_scalar_t_conorms(port_oracle):
         p = 0.0 if p is None else p
         for a in (0.0, 1e-4, 0.05, 0.3, 0.6, 0.95, 0.9999):
             for b in (1e-5, 0.01, 0.3, 0.6, 0.99):
-                e, g = port_oracle.t_conorm_forward(tid, a, b, 0, p), ext.t_conorm_forward(tid, a, b, 0, p)
-                assert abs(g - e) <= 2e-6, ('fold', tname, a, b, g, e)
+                e, g, h = port_oracle.t_conorm_forward(tid, a, b, 0, p), _dev_scalar(2, tid, a, b, p=p), ext.t_conorm_forward(tid, a, b, 0, p)
+                assert abs(g - e) <= 2e-6 and abs(g - h) <= 2e-6, ('fold', tname, a, b, g, e, h)
                 A = max(a, b)
-                e, g = port_oracle.t_conorm_backward(tid, A, b, 0, p), ext.t_conorm_backward(tid, A, b, 0, p)
-                assert abs(g - e) <= 1e-4 * max(1.0, abs(e)), ('dS', tname, A, b, g, e)
+                e, g, h = port_oracle.t_conorm_backward(tid, A, b, 0, p), _dev_scalar(3, tid, A, b, p=p), ext.t_conorm_backward(tid, A, b, 0, p)
+                assert abs(g - e) <= 1e-4 * max(1.0, abs(e)) and abs(g - h) <= 1e-4 * max(1.0, abs(h)), ('dS', tname, A, b, g, e, h)
 
 
 def test_known_answers_survey(port_oracle):
-    """S(0.3, 0.6) and CDF/PDF samples recorded in SURVEY.md 8(c) from the reference's own host functions."""
+    """S(0.3, 0.6) and CDF/PDF samples recorded in SURVEY.md 8(c) from the reference's own host functions (device instantiation)."""
     _dev()
-    from gendr_b200.cuda import generalized_renderer as ext
     for tid, p, want in ((2, 0., 0.72), (3, 0., 0.7627118), (4, 2., 0.7627119), (5, 2., 0.7375257), (6, 2., 0.6708204),
                          (7, 2., 0.6259115), (8, 2., 0.6093786), (9, -2., 0.6296504)):
-        assert abs(ext.t_conorm_forward(tid, 0.3, 0.6, 0, p) - want) < 2e-6
+        assert abs(_dev_scalar(2, tid, 0.3, 0.6, p=p) - want) < 2e-6
     for did, lo, hi, pdf in ((4, 0.460172, 0.539828, 3.969525), (6, 0.475021, 0.524979, 2.49376), (8, 0.468274, 0.531726, 3.151583), (1, 0.45, 0.55, 5.0)):
-        assert abs(ext.sigmoid_forward(did, -1., .01, .1, 1., 0.) - lo) < 2e-6
-        assert abs(ext.sigmoid_forward(did, 1., .01, .1, 1., 0.) - hi) < 2e-6
-        assert abs(ext.sigmoid_backward(did, 1., .01, .1, 1., 0.) - pdf) < 2e-5
+        assert abs(_dev_scalar(0, did, -1., .01, .1, 1., 0.) - lo) < 2e-6
+        assert abs(_dev_scalar(0, did, 1., .01, .1, 1., 0.) - hi) < 2e-6
+        assert abs(_dev_scalar(1, did, 1., .01, .1, 1., 0.) - pdf) < 2e-5
 
 
 def test_shared_reciprocal_division_is_ieee_exact():
