@@ -58,6 +58,7 @@ SIGNATURES = {
     'gendr_voxelize_workspace_bytes': (_SZ, [_I, _I]),
     'gendr_voxelize': (_I, [_P, _P, _I, _I, _I, _P, _SZ, _P]),
     'gendr_render_forward_backward_host': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _PP]),
+    'gendr_release_host_scratch': (None, []),
     'gendr_sigmoid_forward': (_F, [_I, _F, _F, _F, _F, _F]),
     'gendr_sigmoid_backward': (_F, [_I, _F, _F, _F, _F, _F]),
     'gendr_t_conorm_forward': (_F, [_I, _F, _F, _I, _F]),

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -108,6 +109,13 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     if ((long long)B * F >= (1ll << 31) || (long long)B * u->image_size * u->image_size >= (1ll << 31)) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->dist_func < 0 || u->dist_func >= D_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
     if (u->aggr_alpha_func < 0 || u->aggr_alpha_func >= T_COUNT) return GENDR_ERR_INVALID_ARGUMENT;
+    // aggr_rgb_func: 0 hard / 1 softmax; texture_type: 0 surface / 1 vertex (functional/renderer.py:81-83, renderer.py:39-42 raise
+    // ValueError for anything else; a stray id would silently render the background here).  Vertex textures are exactly 3 colours
+    // per face (K.cu:186-190 reads texture[0..8]).  Surface textures with a non-square T are accepted like the reference accepts
+    // them (texture_res = int(sqrt(T)), K.cu:1098: T = 2, 3 behave as texture_res 1 with texel indices 0 and 1 inside the face).
+    if (u->aggr_rgb_func < 0 || u->aggr_rgb_func > 1) return GENDR_ERR_INVALID_ARGUMENT;
+    if (u->texture_type < 0 || u->texture_type > 1) return GENDR_ERR_INVALID_ARGUMENT;
+    if (u->texture_type == 1 && T != 3) return GENDR_ERR_INVALID_ARGUMENT;
     memset(&P, 0, sizeof P);
     P.B = B; P.F = F; P.S = u->image_size; P.T = T;
     P.R = (int)sqrt((double)T);                          // K.cu:1098
@@ -129,15 +137,31 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
     P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
-    P.super_chunk = F < 4096 ? ((F + 255) / 256) * 256 : 4096;     // index list of 8 KB next to the 44 KB wave buffer: 4 CTAs/SM
+    P.super_chunk = F < 2048 ? ((F + 255) / 256) * 256 : 2048;     // index list of 4 KB next to the wave buffers: 4 CTAs/SM
     if (P.super_chunk < 256) P.super_chunk = 256;
     return 0;
 }
 
-static size_t smem_bytes(const RenderParams& P) {
+static size_t smem_bytes(const RenderParams& P, bool face_stationary_backward) {
     const int n_sc = P.super_chunk;
     const int Fw = ((n_sc + NWARPS - 1) / NWARPS + 31) & ~31;
-    return smem_fixed_bytes() + (size_t)NWARPS * Fw * 2;
+    const size_t fixed = face_stationary_backward ? smem_fixed_bytes<BWD_WAVE, NPIX_BWD>() : smem_fixed_bytes<WAVE_FACES, 0>();
+    return fixed + (size_t)NWARPS * Fw * 2;
+}
+
+// Backward kernel choice by measured density regime.  Face-stationary (one reduction per face per CTA, pixel state in shared
+// memory) wins when most staged faces reach most blocks of a tile -- heavy-tailed distributions, wide dist_scale: measured C4
+// 103 vs 112 ms at B = 16 -- pixel-stationary (pixel state in registers, one reduction per face per warp) when faces touch only
+// a few blocks -- C3: 5.97 vs 6.38 ms at B = 64.  The switch is the distribution's cull distance in pixels (>= 2 tiles => dense).
+// GENDR_B200_BWD=ps|fs forces one of them (A/B measurements).
+static int backward_mode(const RenderParams& P) {
+    static const int forced = [] {
+        const char* e = getenv("GENDR_B200_BWD");
+        return (e && strcmp(e, "ps") == 0) ? 1 : ((e && strcmp(e, "fs") == 0) ? 0 : -1);
+    }();
+    if (forced >= 0) return forced;
+    const float reach_px = fminf(P.cull_radius, P.sqrt_thr) * 0.5f * (float)P.S;      // NaN / INF compare false => dense
+    return (reach_px < 2.f * TILE_W) ? 1 : 0;
 }
 
 struct DeviceScope {   // run on the device that owns the data, restore the caller's device afterwards
@@ -174,12 +198,14 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     if (P.B == 0) return 0;
     LaunchCfg cfg;
     cfg.grid = dim3((unsigned)(P.B * P.tiles_x * P.tiles_y));
-    cfg.smem = smem_bytes(P);
+    cfg.bwd_mode = backward ? backward_mode(P) : 0;
+    cfg.smem = smem_bytes(P, backward && cfg.bwd_mode == 0);
     cfg.stream = st;
     cfg.backward = backward;
-    cfg.fast = (P.aggr_rgb_func == 1 && P.texture_type == 0 && !P.dist_squared &&
-                (P.aggr_alpha_func == T_PROBABILISTIC || P.aggr_alpha_func == T_EINSTEIN));
-    cfg.tcn_mode = cfg.fast ? P.aggr_alpha_func : (P.aggr_alpha_func >= T_HAMACHER ? 1 : 0);
+    const bool yager2 = (P.aggr_alpha_func == T_YAGER && P.tcn_p == 2.f);
+    cfg.fast = (P.aggr_rgb_func == 1 && P.texture_type == 0 && P.T == 1 && !P.dist_squared &&
+                (P.aggr_alpha_func == T_PROBABILISTIC || P.aggr_alpha_func == T_EINSTEIN || yager2));
+    cfg.tcn_mode = cfg.fast ? (yager2 ? 4 : P.aggr_alpha_func) : (P.aggr_alpha_func >= T_HAMACHER ? 1 : 0);
     cudaError_t e = kLaunchTable[P.dist_func](P, io, cfg);
     g_launches++;
     if (e != cudaSuccess) return fail((int)e, backward ? "backward render_kernel launch" : "forward render_kernel launch");
@@ -255,7 +281,7 @@ __global__ void probe_kernel(const __grid_constant__ RenderParams P, const float
     PairGeom g;
     const float xp = xy[2 * i], yp = xy[2 * i + 1];
     pair_barycentric(g, rec, xp, yp);
-    pair_project(g, rec, xp, yp, __float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+    pair_project<false>(g, rec, xp, yp, __float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
     float* o = out + (size_t)i * 10;
     o[0] = g.w0; o[1] = g.w1; o[2] = g.w2; o[3] = g.t0; o[4] = g.t1; o[5] = g.t2; o[6] = g.dx; o[7] = g.dy; o[8] = g.sign;
     o[9] = sop2(g.dx, g.dx, g.dy, g.dy);
@@ -279,9 +305,9 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
 }
 
 // ---- cached device scratch for the host-buffer entry point -----------------------------------------------------
-struct HostPathScratch {
+struct HostPathScratch {      // one per device (process-wide): a process may drive several GPUs, each call uses its current device's
     std::mutex mu;
-    int device = -1;
+    bool ready = false;
     size_t cap = 0;
     char* base = nullptr;
     cudaStream_t stream = nullptr;                 // compute
@@ -289,7 +315,8 @@ struct HostPathScratch {
     static const int MAX_CHUNKS = 8;
     cudaEvent_t in_ready[MAX_CHUNKS] = {}, done[MAX_CHUNKS] = {};
 };
-static HostPathScratch g_scratch;
+static const int kMaxDevices = 64;
+static HostPathScratch g_scratch_of[kMaxDevices];
 
 }  // namespace gendr
 
@@ -338,6 +365,7 @@ static int gendr_backward_render_chunk(const float* faces, const float* textures
     io.textures = textures; io.tex_elems = tex_elems;
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_soft_colors; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
+    io.grad_batch_stride_f = (long long)num_faces * 9;
     return run_render(P, io, true, st);
 }
 
@@ -387,6 +415,7 @@ int gendr_backward_render(const float* faces, const float* textures, const float
     io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_soft_colors; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
+    io.grad_batch_stride_f = (long long)num_faces * 9;
     return run_render(P, io, true, st);
 }
 
@@ -404,10 +433,12 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const bool bwd = h_grad_soft_colors && h_grad_faces;
     const size_t need = al(n_faces) * 2 + al(n_tex) * 2 + al(n_col) * 2 + al(n_agg) + al(n_ws);
-    std::lock_guard<std::mutex> lock(g_scratch.mu);
     int dev = 0;
     GENDR_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
-    if (g_scratch.device != dev || !g_scratch.stream) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(GENDR_ERR_INVALID_ARGUMENT, "device ordinal out of range for the host-buffer path");
+    HostPathScratch& g_scratch = g_scratch_of[dev];
+    std::lock_guard<std::mutex> lock(g_scratch.mu);
+    if (!g_scratch.ready) {
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.h2d, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.d2h, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -415,13 +446,13 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
             GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.in_ready[i], cudaEventDisableTiming), "cudaEventCreate");
             GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.done[i], cudaEventDisableTiming), "cudaEventCreate");
         }
+        g_scratch.ready = true;
     }
-    if (g_scratch.device != dev || g_scratch.cap < need) {
-        if (g_scratch.base) { cudaSetDevice(g_scratch.device); cudaFree(g_scratch.base); cudaSetDevice(dev); g_scratch.base = nullptr; g_scratch.cap = 0; }
+    if (g_scratch.cap < need) {
+        if (g_scratch.base) { cudaFree(g_scratch.base); g_scratch.base = nullptr; g_scratch.cap = 0; }
         GENDR_CUDA(cudaMalloc(&g_scratch.base, need), "cudaMalloc of host-path scratch");
         g_scratch.cap = need;
     }
-    g_scratch.device = dev;
     char* p = g_scratch.base;
     float* d_faces = (float*)p; p += al(n_faces);
     float* d_gfaces = (float*)p; p += al(n_faces);
@@ -461,6 +492,26 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     return 0;
 }
 
+void gendr_release_host_scratch(void) {
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    for (int d = 0; d < kMaxDevices; ++d) {
+        HostPathScratch& sc = g_scratch_of[d];
+        std::lock_guard<std::mutex> lock(sc.mu);
+        if (!sc.ready && !sc.base) continue;
+        if (cudaSetDevice(d) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        if (sc.ready) {
+            cudaStreamSynchronize(sc.stream); cudaStreamSynchronize(sc.h2d); cudaStreamSynchronize(sc.d2h);
+            cudaStreamDestroy(sc.stream); cudaStreamDestroy(sc.h2d); cudaStreamDestroy(sc.d2h);
+            for (int i = 0; i < HostPathScratch::MAX_CHUNKS; ++i) { cudaEventDestroy(sc.in_ready[i]); cudaEventDestroy(sc.done[i]); }
+            sc.stream = sc.h2d = sc.d2h = nullptr;
+            sc.ready = false;
+        }
+        if (sc.base) { cudaFree(sc.base); sc.base = nullptr; sc.cap = 0; }
+    }
+    cudaSetDevice(prev);
+}
+
 static int check_aa(const RenderParams& P, const void* pooled_or_flag) {
     if (pooled_or_flag && (P.S & 1)) return fail(GENDR_ERR_INVALID_ARGUMENT, "anti-aliasing needs an even (supersampled) image_size");
     return 0;
@@ -497,7 +548,7 @@ static int backward_indexed_impl(const RenderParams& P, const int* face_index, i
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_soft_colors; io.grad_textures = grad_textures; io.grad_pooled = grad_is_pooled ? 1 : 0;
     io.grad_vertices = grad_vertices; io.face_index = face_index; io.index_batch_stride = index_shared ? 0 : (long long)P.F * 3;
-    io.num_vertices = num_vertices;
+    io.num_vertices = num_vertices; io.grad_batch_stride_v = (long long)num_vertices * 3;
     return run_render(P, io, true, st);
 }
 
@@ -582,6 +633,7 @@ int gendr_backward_render_aa(const float* faces, const float* textures, const fl
     io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_pooled_colors; io.grad_pooled = 1; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
+    io.grad_batch_stride_f = (long long)num_faces * 9;
     return run_render(P, io, true, st);
 }
 

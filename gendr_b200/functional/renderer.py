@@ -90,6 +90,24 @@ class GenDRFunction(Function):
         return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 18
 
 
+# Face indices are checked ONCE per index tensor object (one min/max reduction + host sync; a mesh keeps its faces tensor across
+# iterations, and the mark is invalidated by in-place modification through the tensor's version counter): torch's own gather --
+# vertices.reshape(B*V, 3)[faces] in gendr/functional/face_vertices.py:27 -- raises on an out-of-range index, the fused kernels
+# clamp, so a malformed mesh must fail here instead of rendering silently.
+def check_face_indices(faces, num_vertices):
+    mark = (faces._version, int(num_vertices))
+    if getattr(faces, '_gendr_validated', None) == mark:
+        return
+    if faces.numel():
+        lo, hi = int(faces.min()), int(faces.max())
+        if lo < 0 or hi >= num_vertices:
+            raise IndexError('face index out of range: faces span [%d, %d] but the mesh has %d vertices' % (lo, hi, num_vertices))
+    try:
+        faces._gendr_validated = mark
+    except AttributeError:      # exotic tensor subclasses without a __dict__: validate every call
+        pass
+
+
 class GenDRIndexedFunction(Function):
     """render() for an indexed mesh: (vertices [B,V,3] screen space, faces [B,F,3] or [F,3] int) instead of the gathered
     face_vertices [B,F,3,3].  The gather runs inside the face preprocessing kernel and the gradient is scatter-added
@@ -110,6 +128,7 @@ class GenDRIndexedFunction(Function):
             TEXTURE_TYPE_IDS[texture_type], background_color)
         verts = vertices.detach().to(torch.float32).contiguous()
         B, V = verts.shape[:2]
+        check_face_indices(faces, V)
         index = faces.detach().to(device=verts.device, dtype=torch.int32).contiguous()
         shared = index.ndimension() == 2
         F = index.shape[-2]
@@ -214,6 +233,7 @@ class GenDRSceneFunction(Function):
         verts = vertices.detach().to(torch.float32).contiguous()
         dev = verts.device
         B, V = verts.shape[:2]
+        check_face_indices(faces, V)
         index = faces.detach().to(device=dev, dtype=torch.int32).contiguous()
         shared = index.ndimension() == 2
         F = index.shape[-2]
@@ -279,4 +299,7 @@ def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, im
     light = make_light_params(**lighting) if lighting is not None else None
     if not torch.is_tensor(eyes):
         eyes = torch.tensor(eyes, dtype=torch.float32, device=vertices.device)
+    if eyes.requires_grad:
+        raise ValueError('render_scene does not differentiate w.r.t. the camera position: use LookAt/Look (torch path) for eyes that '
+                         'require a gradient (experiments/opt_camera.py)')
     return GenDRSceneFunction.apply(vertices, faces, textures, eyes, cam, light, params, anti_aliasing)

@@ -57,7 +57,11 @@ class Mesh(object):
             self.texture_res = int(np.sqrt(self._textures.shape[2]))
 
     @classmethod
-    def from_obj(cls, filename_obj, normalization=False, texture_res=1, texture_type='surface'):
+    def from_obj(cls, filename_obj, normalization=False, load_texture=False, texture_res=1, texture_type='surface'):
+        """Positional signature of gendr.Mesh.from_obj (gendr/mesh.py:62-81); OBJ/MTL texture loading is the asset pipeline
+        (out of scope), so load_texture=True raises instead of silently ignoring the request."""
+        if load_texture:
+            raise NotImplementedError('gendr_b200.Mesh.from_obj: load_texture=True (OBJ/MTL texture loading) is not part of the hot path')
         vertices, faces = functional.load_obj(filename_obj, normalization=normalization)
         dev = _default_device()
         return cls(vertices.to(dev), faces.to(dev), None, texture_res, texture_type)

@@ -56,9 +56,16 @@ class _EyeCamera(Transform):
     def forward(self, mesh):
         if (_mesh.FUSE_SCENE and mesh._pending_camera is None and mesh._vertices.is_cuda and mesh.texture_type == 'surface'
                 and self._fusable_eye(mesh) is not None and self._fused_camera() is not None):
-            # deferred: GenDR.forward runs the camera kernel (or .vertices materialises it with transform())
+            # deferred: GenDR.forward runs the camera kernel (or .vertices materialises it with transform()).  The reference
+            # transforms eagerly, so the camera is SNAPSHOT here: later in-place changes of the eye tensor / attributes of this
+            # module must not reach the deferred step.
+            cam = copy.copy(self)
+            eye = self._eye
+            cam._eye = eye.detach().clone() if torch.is_tensor(eye) else copy.deepcopy(eye)
+            if hasattr(cam, 'camera_direction'):
+                cam.camera_direction = copy.deepcopy(self.camera_direction)
             return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,
-                        _pending_light=mesh._pending_light, _pending_camera=copy.copy(self))
+                        _pending_light=mesh._pending_light, _pending_camera=cam)
         return super().forward(mesh)
 
 

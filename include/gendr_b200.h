@@ -170,10 +170,13 @@ int gendr_voxelize(const float* faces, int* voxels, int batch, int num_faces, in
 
 /* End-to-end convenience with HOST buffers (pinned or pageable): H2D copies of faces/textures/grad_soft_colors,
  * forward + backward on the current device, D2H copies of soft_colors/grad_faces/grad_textures, one stream
- * synchronisation at the end.  Device scratch is cached inside the library between calls. */
+ * synchronisation at the end.  Device scratch is cached inside the library between calls (per device). */
 int gendr_render_forward_backward_host(const float* h_faces, const float* h_textures, const float* h_grad_soft_colors,
                                        float* h_soft_colors, float* h_grad_faces, float* h_grad_textures,
                                        int batch, int num_faces, int texture_size, const gendr_render_params* params);
+/* The scratch (device buffers, three streams, events) is kept PER DEVICE -- the call uses the current device's -- so one process
+ * may drive several GPUs; this frees all of it (every device), e.g. before a fork or at shutdown. */
+void gendr_release_host_scratch(void);
 
 /* Scalar functions of the reference module.  Like the reference's (host instantiations of __host__ __device__ templates,
  * K.cu:1230-1270) they run on the CPU: no device, no launch, no allocation -- animations/distributions_to_csv.py:19 calls them

@@ -1,0 +1,117 @@
+"""C-ABI robustness on the GPU box: argument validation, the host-buffer entry point and its per-device scratch, non-square
+surface textures (T = 2, 3 behave like the reference: texture_res = int(sqrt(T)) = 1), index validation of the fused paths."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+from gendr_b200 import _lib
+from gendr_b200.cuda import generalized_renderer as ext
+
+pytestmark = pytest.mark.gpu
+INVALID = 100001
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda:0')
+
+
+def _call_forward(dev, params, T=1, F=4, B=1, S=16):
+    lib = _lib.load()
+    faces = torch.rand(B, F, 9, device=dev)
+    tex = torch.rand(B, F, T, 3, device=dev)
+    colors, aggrs = torch.empty(B, 4, S, S, device=dev), torch.empty(B, 2, S, S, device=dev)
+    ws = torch.empty(lib.gendr_workspace_bytes(B, F), dtype=torch.uint8, device=dev)
+    return lib.gendr_forward_render(faces.data_ptr(), tex.data_ptr(), None, aggrs.data_ptr(), colors.data_ptr(), B, F, T, C.byref(params), 0,
+                                    ws.data_ptr(), ws.numel(), None)
+
+
+def test_invalid_ids_are_rejected():
+    dev = _dev()
+    ok = ext.make_params(16, 6, 0.02, False, 0., 0., 1e4, 2, 0., 1, 1e-3, 1e-3, 1., 100., True, 0)
+    assert _call_forward(dev, ok) == 0
+    for field, value, T in (('aggr_rgb_func', 2, 1), ('aggr_rgb_func', -1, 1), ('texture_type', 2, 1), ('texture_type', -1, 1),
+                            ('dist_func', 18, 1), ('aggr_alpha_func', 10, 1), ('image_size', 0, 1)):
+        p = ext.make_params(16, 6, 0.02, False, 0., 0., 1e4, 2, 0., 1, 1e-3, 1e-3, 1., 100., True, 0)
+        setattr(p, field, value)
+        assert _call_forward(dev, p, T=T) == INVALID, (field, value)
+        assert b'invalid argument' in _lib.load().gendr_last_error()
+    # vertex textures are exactly three colours per face (K.cu:186-190)
+    pv = ext.make_params(16, 6, 0.02, False, 0., 0., 1e4, 2, 0., 1, 1e-3, 1e-3, 1., 100., True, 1)
+    assert _call_forward(dev, pv, T=3) == 0
+    for T in (1, 2, 4, 9):
+        assert _call_forward(dev, pv, T=T) == INVALID
+    with pytest.raises(_lib.GendrCudaError):
+        _lib.check(_call_forward(dev, pv, T=4))
+
+
+def test_non_square_surface_textures_match_the_oracle(port_oracle):
+    """T = 2 and T = 3 surface textures: texture_res = int(sqrt(T)) = 1 (K.cu:1098), texel index 1 is the face's OWN second texel
+    and receives gradient (K.cu:201) -- not the single-texel fast path."""
+    dev = _dev()
+    import gendr_b200 as gd
+    from oracle.cpu_oracle import make_params
+    port_oracle.lib.gendr_oracle_set_mode(1)
+    try:
+        fv, _ = scenes.soup(80, batch=2, seed=21, size=0.15)
+        gen = torch.Generator().manual_seed(5)
+        g = torch.randn(2, 4, 40, 40, generator=gen)
+        for T in (2, 3):
+            ft = torch.rand(2, fv.shape[1], T, 3, generator=gen)
+            for rgb in ('softmax', 'hard'):
+                kw = dict(image_size=40, dist_func='logistic', aggr_alpha_func='probabilistic', dist_scale=0.03, aggr_rgb_func=rgb)
+                a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
+                img = gd.functional.render(a, b, **kw)
+                img.backward(g.to(dev))
+                p = make_params(**kw)
+                f = port_oracle.forward(fv.numpy(), ft.numpy(), p)
+                gf, gt = port_oracle.backward(f, g.numpy(), p)
+                assert np.abs(img.detach().cpu().numpy() - f['soft_colors']).max() <= 2e-5
+                gtn = b.grad.cpu().numpy().reshape(gt.shape)
+                assert np.abs(gtn - gt).max() <= 1e-4 * np.abs(gt).max() + 1e-7, (T, rgb)
+                assert np.abs(a.grad.cpu().numpy().reshape(gf.shape) - gf).max() <= 1e-4 * np.abs(gf).max()
+                assert np.abs(gtn.reshape(2, -1, T, 3)[:, :, 1:]).max() > 0 or rgb == 'hard'      # the second texel does get gradient
+    finally:
+        port_oracle.lib.gendr_oracle_set_mode(0)
+
+
+def test_host_buffer_entry_point_and_scratch_release():
+    dev = _dev()
+    lib = _lib.load()
+    fv, ft = scenes.soup(60, batch=2, seed=3, size=0.1)
+    B, F = fv.shape[:2]
+    S = 32
+    params = ext.make_params(S, 4, 0.02, False, 0., 0., 1e4, 3, 0., 1, 1e-3, 1e-3, 1., 100., False, 0)
+    g = torch.randn(B, 4, S, S, generator=torch.Generator().manual_seed(1))
+    h_col, h_gf, h_gt = torch.empty(B, 4, S, S), torch.empty(B, F, 9), torch.empty(B, F, 1, 3)
+    for _ in range(2):      # second round re-creates the scratch after the release
+        _lib.check(lib.gendr_render_forward_backward_host(fv.contiguous().data_ptr(), ft.contiguous().data_ptr(), g.data_ptr(), h_col.data_ptr(),
+                                                          h_gf.data_ptr(), h_gt.data_ptr(), B, F, 1, C.byref(params)))
+        import gendr_b200 as gd
+        a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
+        img = gd.functional.render(a, b, image_size=S, dist_func='gaussian', aggr_alpha_func='einstein', dist_scale=0.02, double_side=False)
+        img.backward(g.to(dev))
+        assert torch.equal(img.detach().cpu(), h_col)
+        assert torch.allclose(a.grad.cpu().view(B, F, 9), h_gf, rtol=1e-4, atol=1e-5 * float(h_gf.abs().max()))
+        lib.gendr_release_host_scratch()
+
+
+def test_fused_paths_validate_face_indices():
+    dev = _dev()
+    import gendr_b200 as gd
+    verts, faces = scenes.icosphere(1)
+    v = (verts * 0.5)[None].to(dev) + torch.tensor([0., 0., 3.], device=dev)
+    tex = torch.ones(1, faces.shape[0], 1, 3, device=dev)
+    gd.functional.render_indexed(v, faces.to(dev), tex, image_size=16)
+    bad = faces.clone(); bad[0, 0] = verts.shape[0]
+    with pytest.raises(IndexError):
+        gd.functional.render_indexed(v, bad.to(dev), tex, image_size=16)
+    neg = faces.clone(); neg[1, 1] = -1
+    with pytest.raises(IndexError):
+        gd.functional.render_scene(v, neg.to(dev), tex, [0., 0., -3.], image_size=16)
+    with pytest.raises(ValueError):
+        gd.functional.render_scene(v, faces.to(dev), tex, torch.tensor([0., 0., -3.], device=dev, requires_grad=True), image_size=16)

@@ -50,6 +50,7 @@ def main():
     if '--out' in sys.argv:
         out = sys.argv[sys.argv.index('--out') + 1]
     quick = '--quick' in sys.argv
+    only = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else None
     import gendr_b200 as gd
     dev = torch.device('cuda:0')
     ref = load_reference()
@@ -70,6 +71,8 @@ def main():
     result = {'criterion': '|d| <= 1e-4*|ref| + atol; atol = 1e-5 (RGBA), 1e-4*max|ref| (gradients)', 'gpu': torch.cuda.get_device_name(0),
               'cases': {}}
     for name, fv, ft, kw in cases:
+        if only and not name.startswith(only):
+            continue
         t0 = time.time()
         fv, ft = scenes.with_sentinel(fv, ft)
         B, S = fv.shape[0], kw['image_size']
