@@ -65,6 +65,26 @@ def workload(name, batch, rank=0, world=1):
     return fv, ft, kw, desc, b
 
 
+PARAMS_NOTE = 'GenDR defaults (dist_scale 1e-2, dist_eps 1e4, softmax RGB, eps=gamma=1e-3, near 1, far 100, single-sided)'
+
+
+def common_config(desc, B, world, F, S):
+    """The `config` object is IDENTICAL in both arms (the driver compares them); arm-specific remarks go under `notes`."""
+    return {'workload': desc, 'per_gpu_batch': B, 'global_batch': B * world, 'faces': F, 'image_size': S, 'texture_res': 1, 'params': PARAMS_NOTE}
+
+
+def csrc_sha():
+    """Fingerprint of the kernel sources: ncu-derived constants in profiles/roofline_traffic.json are only used when they were
+    captured from exactly these sources."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'gendr_b200', 'csrc')
+    for name in sorted(os.listdir(d)):
+        if name.endswith(('.cu', '.cuh')):
+            h.update(open(os.path.join(d, name), 'rb').read())
+    return h.hexdigest()[:16]
+
+
 def algorithmic_bytes(B, F, S, T):
     """compulsory HBM traffic of the path (faces+textures read twice, grads written once, RGBA+aggrs
     written then read, cotangent read)."""
@@ -173,8 +193,9 @@ def reference_arm(args):
         else:
             line.update({'steps': 2, 'warmup': 1})
         line.update({'value': cpu['value'], 'ms_per_step': cpu['ms_per_step'], 'gpu_launches': 0,
-                     'config': {'workload': desc, 'per_gpu_batch': b, 'timed_on': 'host CPU cores: the reference CUDA kernels compiled for the host '
-                                '(oracle/_ref) -- no GPU or no baseline/_ref build available'},
+                     'config': common_config(desc, b, 1, F, S),
+                     'notes': {'timed_on': 'host CPU cores: the reference CUDA kernels compiled for the host (oracle/_ref) -- no GPU or no '
+                                           'baseline/_ref build available'},
                      'cpu_baseline': {k: cpu[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
                      'e2e': {'value': cpu['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
         return line
@@ -229,10 +250,10 @@ def reference_arm(args):
         e2e_step()
     e2e_s = (time.perf_counter() - w0) / n_e2e
     line.update({'value': pairs / (ms * 1e-3) / 1e6, 'ms_per_step': ms, 'steps': steps, 'warmup': warm,
-                 'config': {'workload': desc, 'per_gpu_batch': B, 'global_batch': B, 'faces': F, 'image_size': S,
-                            'timed_on': "one B200: the reference's own CUDA kernels (unmodified sources, sm_100a build under baseline/_ref) through "
-                                        'gendr.functional.render + backward; the reference has no multi-GPU path, so the arm is always 1 GPU',
-                            'steps_note': 'steps/warmup clamped (one reference step takes seconds)'},
+                 'config': common_config(desc, B, 1, F, S),
+                 'notes': {'timed_on': "one B200: the reference's own CUDA kernels (unmodified sources, sm_100a build under baseline/_ref) through "
+                                       'gendr.functional.render + backward; the reference has no multi-GPU path, so the arm is always 1 GPU',
+                           'steps_note': 'steps/warmup clamped (one reference step takes seconds)'},
                  'e2e': {'value': pairs / e2e_s / 1e6, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
                          'h2d_bytes_per_step': int((h_fv.numel() + h_ft.numel() + h_g.numel()) * 4),
                          'd2h_bytes_per_step': int((h_img.numel() + h_gf.numel() + h_gt.numel()) * 4)},
@@ -261,6 +282,129 @@ def emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
+class Rig:
+    """Device-resident buffers of one workload on this rank + the two step flavours (raw C-ABI calls on preallocated buffers)."""
+
+    def __init__(self, name, batch, rank, world, dev):
+        import torch
+        from gendr_b200.cuda import generalized_renderer as ext
+        from gendr_b200.functional import renderer as fr
+        self.ext, self.torch = ext, torch
+        self.fv, self.ft, self.kw, self.desc, self.B = workload(name, batch, rank, world)
+        fv, ft, kw, B = self.fv, self.ft, self.kw, self.B
+        self.F, self.S, self.T = fv.shape[1], kw['image_size'], ft.shape[2]
+        F, S, T = self.F, self.S, self.T
+        self.params = ext.make_params(S, fr.DIST_FUNC_IDS[kw['dist_func']], 1e-2, False, None, None, 1e4, fr.AGGR_ALPHA_FUNC_IDS[kw['aggr_alpha_func']],
+                                      kw.get('aggr_alpha_t_conorm_p'), 1, 1e-3, 1e-3, 1, 100, kw['double_side'], 0, (0, 0, 0))
+        self.faces = fv.to(dev).view(B, F, 9).contiguous()
+        self.tex = ft.to(dev).contiguous()
+        self.gcol = torch.randn(B, 4, S, S, generator=torch.Generator().manual_seed(2 + rank)).to(dev)
+        self.colors = torch.empty(B, 4, S, S, device=dev)
+        self.aggrs = torch.empty(B, 2, S, S, device=dev)
+        self.gfaces = torch.empty(B, F, 9, device=dev)
+        self.gsum = torch.empty(F, 9, device=dev)          # batch-summed gradient of the shared mesh (N > 1)
+        self.gtex = torch.empty(B, F, T, 3, device=dev)
+        self.ws = ext.workspace_for(self.faces)
+
+    def step_single(self, ev=None):
+        """N = 1: forward + backward with per-item gradients [B,F,9] -- exactly what the reference arm produces."""
+        ext = self.ext
+        ext.forward_render_raw(self.faces, self.tex, None, self.aggrs, self.colors, self.params, False, self.ws)
+        if ev:
+            ev[0].record()
+        ext.backward_render_raw(self.faces, self.tex, self.colors, self.aggrs, self.gfaces, self.gtex, self.gcol, self.params, self.ws, True, True)
+        if ev:
+            ev[1].record()
+
+    def step_sharded(self, ev=None):
+        """N > 1 (one mesh shared by all views): the backward kernel accumulates the gradient of the shared geometry
+        straight into ONE [F,9] buffer (gendr_backward_render_batchsum) and that buffer goes to the single all-reduce -- no
+        [B,F,9] intermediate, no reduction kernel."""
+        import torch.distributed as dist
+        ext = self.ext
+        ext.forward_render_raw(self.faces, self.tex, None, self.aggrs, self.colors, self.params, False, self.ws)
+        if ev:
+            ev[0].record()
+        ext.backward_render_batchsum_raw(self.faces, self.tex, self.colors, self.aggrs, self.gsum, self.gtex, self.gcol, self.params, self.ws, True, True)
+        if ev:
+            ev[1].record()
+        dist.all_reduce(self.gsum, op=dist.ReduceOp.SUM)
+        if ev:
+            ev[2].record()
+
+
+def timed_run(rig, steps, warmup, world, dev, local_rank, lib):
+    """W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    step = rig.step_sharded if world > 1 else rig.step_single
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.gendr_launch_count()
+    evs = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    w_begin = time.perf_counter()
+    t_begin.record()
+    for i in range(steps):
+        step(evs[i])
+    t_end.record()
+    torch.cuda.synchronize()
+    sampler.window(w_begin, time.perf_counter())
+    if world > 1:
+        dist.barrier()
+    launches = lib.gendr_launch_count() - launches0
+    clocks = sampler.stop()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    bwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    allreduce_ms = (sum(e[1].elapsed_time(e[2]) for e in evs) / steps) if world > 1 else 0.0
+    if world > 1:
+        tmax = torch.tensor([elapsed_ms, bwd_ms, allreduce_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        elapsed_ms, bwd_ms, allreduce_ms = (float(x) for x in tmax.tolist())
+    return {'ms_per_step': elapsed_ms / steps, 'bwd_ms': bwd_ms, 'fwd_ms': elapsed_ms / steps - bwd_ms - allreduce_ms, 'allreduce_ms': allreduce_ms,
+            'launches': int(launches), 'clocks': clocks}
+
+
+def sharded_equals_single(rig, rank, world, dev):
+    """Hardware proof that the batch-sharded job computes what one GPU would (SURVEY 8e "Verification"): rank 0 re-renders rank 1's
+    shard itself and compares the images bit for bit with what rank 1 produced; it also recomputes the gradient sum of the WHOLE
+    global batch alone and compares the all-reduced gradient to 1e-4 of its maximum."""
+    import torch
+    import torch.distributed as dist
+    from gendr_b200.cuda import generalized_renderer as ext
+    rig.step_sharded()
+    torch.cuda.synchronize()
+    img_probe = rig.colors[:2].contiguous()                      # first two views of this rank's shard
+    got_from_1 = torch.empty_like(img_probe)
+    if rank == 1:
+        dist.send(img_probe, dst=0)
+    if rank == 0:
+        dist.recv(got_from_1, src=1)
+    out = None
+    if rank == 0:
+        total = torch.zeros_like(rig.gsum)
+        images_equal = True
+        for r in range(world):
+            other = Rig(rig.name, rig.B, r, world, dev)
+            other.step_single()
+            total += other.gfaces.sum(0)
+            if r == 1:
+                images_equal = bool(torch.equal(other.colors[:2], got_from_1))
+            del other
+        torch.cuda.synchronize()
+        scale = float(total.abs().max())
+        err = float((rig.gsum - total).abs().max()) / max(scale, 1e-30)
+        out = {'images_bit_identical': images_equal, 'allreduced_grad_max_err_over_max': err, 'ok': bool(images_equal and err <= 1e-4)}
+    dist.barrier()
+    return out
+
+
 def main():
     args = parse()
     quiet_stdout()
@@ -274,12 +418,9 @@ def main():
         emit(reference_arm(args))
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from gendr_b200 import _lib, parallel
-    from gendr_b200.cuda import generalized_renderer as ext
-    from gendr_b200.functional import renderer as fr
+    from gendr_b200 import _lib
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm')
@@ -289,62 +430,40 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
 
-    fv, ft, kw, desc, B = workload(args.workload, args.batch, rank, world)
-    F, S, T = fv.shape[1], kw['image_size'], ft.shape[2]
-    params = ext.make_params(S, fr.DIST_FUNC_IDS[kw['dist_func']], 1e-2, False, None, None, 1e4, fr.AGGR_ALPHA_FUNC_IDS[kw['aggr_alpha_func']],
-                             kw.get('aggr_alpha_t_conorm_p'), 1, 1e-3, 1e-3, 1, 100, kw['double_side'], 0, (0, 0, 0))
-    faces = fv.to(dev).view(B, F, 9).contiguous()
-    tex = ft.to(dev).contiguous()
-    gcol = torch.randn(B, 4, S, S, generator=torch.Generator().manual_seed(2)).to(dev)
-    colors = torch.empty(B, 4, S, S, device=dev)
-    aggrs = torch.empty(B, 2, S, S, device=dev)
-    gfaces = torch.empty(B, F, 9, device=dev)
-    gtex = torch.empty(B, F, T, 3, device=dev)
-    ws = ext.workspace_for(faces)
-
-    def step(ev=None):
-        ext.forward_render_raw(faces, tex, None, aggrs, colors, params, False, ws)
-        gfaces.zero_(); gtex.zero_()
-        if ev:
-            ev[0].record()
-        ext.backward_render_raw(faces, tex, colors, aggrs, gfaces, gtex, gcol, params, ws, True, False)
-        if ev:
-            ev[1].record()
-        if world > 1:      # shared mesh: gradient w.r.t. the shared geometry = batch sum + ONE all-reduce
-            return parallel.allreduce_shared_face_grads(gfaces.view(B, F, 3, 3))
-        return None
-
-    for _ in range(max(3, args.warmup)):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = lib.gendr_launch_count()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    w_begin = time.perf_counter()
-    t_begin.record()
-    for i in range(args.steps):
-        step(evs[i])
-    t_end.record()
-    torch.cuda.synchronize()
-    sampler.window(w_begin, time.perf_counter())
-    if world > 1:
-        dist.barrier()
-    launches = lib.gendr_launch_count() - launches0
-    clocks = sampler.stop()
-    elapsed_ms = t_begin.elapsed_time(t_end)
-    bwd_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    if world > 1:
-        tmax = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(tmax.item())
-    ms_per_step = elapsed_ms / args.steps
+    rig = Rig(args.workload, args.batch, rank, world, dev)
+    rig.name = args.workload
+    fv, ft, kw, desc, B, F, S, T = rig.fv, rig.ft, rig.kw, rig.desc, rig.B, rig.F, rig.S, rig.T
+    params, faces, tex, gcol, colors = rig.params, rig.faces, rig.tex, rig.gcol, rig.colors
+    warm = max(3, args.warmup)
+    res = timed_run(rig, args.steps, warm, world, dev, local_rank, lib)
+    ms_per_step, bwd_ms, clocks, launches = res['ms_per_step'], res['bwd_ms'], res['clocks'], res['launches']
     pairs_per_step = B * world * S * S * F
     value = pairs_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- the same step through the public Python API (gendr_b200.functional.render + .backward(): autograd node, output allocation,
+    #      ctypes) -- what a user of the module calls; device-resident inputs -------------------------------------------------------
+    import gendr_b200 as gd
+    fv_d, ft_d = faces.view(B, F, 3, 3), tex
+
+    def api_step():
+        a, t = fv_d.detach().requires_grad_(True), ft_d.detach().requires_grad_(True)
+        gd.functional.render(a, t, **kw).backward(gcol)
+        return a.grad
+    for _ in range(3):
+        api_step()
+    torch.cuda.synchronize()
+    n_api = max(3, min(args.steps, 10))
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(n_api):
+        api_step()
+    a1.record()
+    torch.cuda.synchronize()
+    api_ms = a0.elapsed_time(a1) / n_api
+    if world > 1:
+        tmax = torch.tensor([api_ms], device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        api_ms = float(tmax.item())
 
     # ---- e2e: host buffers through the C ABI (H2D + fwd + bwd + D2H every step) ---------------------------------
     h_faces, h_tex, h_gcol = faces.cpu().pin_memory(), tex.cpu().pin_memory(), gcol.cpu().pin_memory()
@@ -371,6 +490,25 @@ def main():
     e2e = {'value': pairs_per_step / e2e_s / 1e6, 'unit': UNIT, 'ms_per_step': e2e_s * 1e3,
            'h2d_bytes_per_step': int((h_faces.numel() + h_tex.numel() + h_gcol.numel()) * 4),
            'd2h_bytes_per_step': int((h_col.numel() + h_gfaces.numel() + h_gtex.numel()) * 4), 'matches_device_path': e2e_ok}
+    del h_faces, h_tex, h_gcol, h_col, h_gfaces, h_gtex
+
+    # ---- N > 1: hardware equality proof + the C4 configuration (the one multi-GPU configuration BASELINE.json names) -----------
+    equal, c4 = None, None
+    if world > 1:
+        equal = sharded_equals_single(rig, rank, world, dev)
+        if args.workload != 'c4':
+            del rig
+            torch.cuda.empty_cache()
+            rig4 = Rig('c4', 0, rank, world, dev)
+            rig4.name = 'c4'
+            r4 = timed_run(rig4, max(2, min(args.steps, 3)), 1, world, dev, local_rank, lib)
+            pairs4 = rig4.B * world * rig4.S * rig4.S * rig4.F
+            c4 = {'workload': rig4.desc, 'per_gpu_batch': rig4.B, 'global_batch': rig4.B * world, 'metric': METRIC, 'unit': UNIT,
+                  'value': pairs4 / (r4['ms_per_step'] * 1e-3) / 1e6, 'ms_per_step': r4['ms_per_step'], 'fwd_ms': r4['fwd_ms'], 'bwd_ms': r4['bwd_ms'],
+                  'allreduce_ms': r4['allreduce_ms'], 'steps': max(2, min(args.steps, 3)), 'warmup': 1, 'clocks': r4['clocks'],
+                  'note': 'C4 of BASELINE.json: 8192 faces, 256x256, cauchy + yager(p=2), 64 views per GPU (512 views on 8 GPUs), one all-reduce of '
+                          'the batch-summed [F,3,3] gradient per step; timed like the headline line (CUDA events, max over ranks)'}
+            del rig4
 
     if rank != 0:
         if world > 1:
@@ -384,15 +522,20 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     fwd_bytes, bwd_bytes = algorithmic_bytes(B, F, S, T)
-    traffic, prof = None, {}
+    traffic, traffic_note, prof = None, None, {}
     try:
-        prof = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get(args.workload, {})
-        if B == 64:          # the ncu capture is of the default per-GPU batch
+        allprof = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
+        prof = allprof.get(args.workload, {})
+        if allprof.get('csrc_sha') != csrc_sha():
+            prof, traffic_note = {}, 'null: the committed ncu capture (profiles/roofline_traffic.json) is of other kernel sources than the ones running'
+        elif B != prof.get('batch', 64):
+            prof, traffic_note = {}, 'null: the committed ncu capture is of per-GPU batch %s' % prof.get('batch', 64)
+        else:
             traffic = prof.get('backward_dram_bytes_per_launch')
     except Exception:
-        pass
+        traffic_note = 'null: profiles/roofline_traffic.json not readable'
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'render_kernel<gaussian,simple,BWD> (backward)' if args.workload == 'c3' else 'render_kernel<...,BWD> (backward)',
+    roofline = {'bound': 'hbm', 'kernel': 'backward render kernel (render_kernel<..,BWD> pixel-stationary or render_bwd_fs_kernel face-stationary, by density)',
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
                 'traffic': traffic, 'algorithmic_bytes_per_launch': bwd_bytes, 'kernel_ms': bwd_ms,
@@ -400,9 +543,11 @@ def main():
                                'frac_of_measured': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak,
                                'frac_of_8TBps_nominal': (fwd_bytes + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / 8000.0},
                 'note': 'all-pairs ALU/SFU-bound path: compulsory traffic is ~0.01 B per pixel*face (SURVEY 8d), so the HBM fraction is small by construction'}
-    if prof.get('backward_warp_instructions') and B == 64 and clocks.get('sm_mhz'):
+    if traffic_note:
+        roofline['traffic_note'] = traffic_note
+    if prof.get('backward_warp_instructions') and clocks.get('sm_mhz'):
         # the roofline that actually binds: warp-instruction issue rate.  Instructions per launch from the committed
-        # ncu capture of this workload (smsp__inst_executed.sum), duration and SM clock measured live in this run.
+        # ncu capture of this workload and these sources (smsp__inst_executed.sum), duration and SM clock measured live in this run.
         peak_issue = 148 * 4 * clocks['sm_mhz'] * 1e6            # 148 SMs x 4 schedulers x 1 warp-instruction per clock
         ach = prof['backward_warp_instructions'] / (bwd_ms * 1e-3)
         roofline['issue_rate'] = {'bound': 'warp-instruction issue (FP32/SFU pipes)', 'achieved': ach / 1e9, 'peak': peak_issue / 1e9,
@@ -410,13 +555,23 @@ def main():
                                   'active_lanes_per_instruction': prof.get('backward_active_lanes_per_instruction'),
                                   'source': 'instructions: profiles/roofline_traffic.json (ncu); time and SM clock: this run'}
 
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+    cfg = common_config(desc, B, world, F, S)
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': desc, 'per_gpu_batch': B, 'global_batch': B * world, 'faces': F, 'image_size': S, 'texture_res': 1,
-                       'params': 'GenDR defaults (dist_scale 1e-2, dist_eps 1e4, softmax RGB, eps=gamma=1e-3, near 1, far 100, single-sided)',
-                       'parallelism': 'batch-sharded dp%d, one all-reduce of the shared-mesh face gradient [F,3,3] per step' % world if world > 1 else 'single GPU',
-                       'l2': 'no flush: per-step working set (records+images+grads ~%d MB) exceeds the 126 MB L2' % ((B * F * 144 + B * S * S * 4 * 10 + B * F * 36 * 2) // 1000000)},
+            'config': cfg,
+            'notes': {'parallelism': ('batch-sharded dp%d: the backward kernel accumulates the shared-mesh gradient into ONE [F,3,3] buffer per rank, '
+                                      'one NCCL all-reduce of it per step' % world) if world > 1 else 'single GPU, per-item gradients [B,F,3,3]',
+                      'l2': 'no flush: per-step working set (records+images+grads ~%d MB) exceeds the 126 MB L2' % ((B * F * 176 + B * S * S * 4 * 10 + B * F * 36 * 2) // 1000000),
+                      'value_is': 'raw C-ABI calls on preallocated device buffers (gendr_forward_render + gendr_backward_render); value_public_api is the '
+                                  'same step through gendr_b200.functional.render(...).backward()'},
+            'value_public_api': {'value': pairs_per_step / (api_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': api_ms},
+            'kernel_ms': {'forward': res['fwd_ms'], 'backward': bwd_ms, 'allreduce': res['allreduce_ms']},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline}
+    if equal is not None:
+        line['sharded_equals_single'] = bool(equal['ok'])
+        line['sharded_check'] = equal
+    if c4 is not None:
+        line['c4'] = c4
 
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_arm(fv, ft, kw, steps=2, warmup=1)

@@ -390,23 +390,21 @@ int gendr_forward_render(const float* faces, const float* textures, float* faces
     return run_render(P, io, false, st);
 }
 
-int gendr_backward_render(const float* faces, const float* textures, const float* soft_colors,
-                          const float* aggrs_info, float* grad_faces, float* grad_textures,
-                          const float* grad_soft_colors, int batch, int num_faces, int texture_size,
-                          const gendr_render_params* params, int workspace_valid, int zero_grads,
-                          void* workspace, size_t workspace_bytes, void* stream) {
+static int backward_render_impl(const char* who, bool batchsum, const float* faces, const float* textures, const float* soft_colors,
+                                const float* aggrs_info, float* grad_faces, float* grad_textures, const float* grad_soft_colors, int batch,
+                                int num_faces, int texture_size, const gendr_render_params* params, int workspace_valid, int zero_grads,
+                                void* workspace, size_t workspace_bytes, void* stream) {
     RenderParams P;
-    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render");
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, who);
     if (batch == 0) return 0;
-    if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_soft_colors || !workspace)
-        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render");
+    if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_soft_colors || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, who);
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
     DeviceScope dev;
     GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (!workspace_valid) if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
     if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
+        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)(batchsum ? 1 : batch) * num_faces * 9 * sizeof(float), st), "zero grad_faces");
         if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
     }
     KernelIO io;
@@ -415,8 +413,27 @@ int gendr_backward_render(const float* faces, const float* textures, const float
     io.textures = textures; io.tex_elems = (long long)batch * num_faces * texture_size * 3;
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_soft_colors; io.grad_faces = grad_faces; io.grad_textures = grad_textures;
-    io.grad_batch_stride_f = (long long)num_faces * 9;
+    io.grad_batch_stride_f = batchsum ? 0 : (long long)num_faces * 9;
     return run_render(P, io, true, st);
+}
+
+int gendr_backward_render(const float* faces, const float* textures, const float* soft_colors,
+                          const float* aggrs_info, float* grad_faces, float* grad_textures,
+                          const float* grad_soft_colors, int batch, int num_faces, int texture_size,
+                          const gendr_render_params* params, int workspace_valid, int zero_grads,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_render_impl("invalid argument to gendr_backward_render", false, faces, textures, soft_colors, aggrs_info, grad_faces, grad_textures,
+                                grad_soft_colors, batch, num_faces, texture_size, params, workspace_valid, zero_grads, workspace, workspace_bytes, stream);
+}
+
+int gendr_backward_render_batchsum(const float* faces, const float* textures, const float* soft_colors,
+                                   const float* aggrs_info, float* grad_faces_sum, float* grad_textures,
+                                   const float* grad_soft_colors, int batch, int num_faces, int texture_size,
+                                   const gendr_render_params* params, int workspace_valid, int zero_grads,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_render_impl("invalid argument to gendr_backward_render_batchsum", true, faces, textures, soft_colors, aggrs_info, grad_faces_sum,
+                                grad_textures, grad_soft_colors, batch, num_faces, texture_size, params, workspace_valid, zero_grads, workspace,
+                                workspace_bytes, stream);
 }
 
 int gendr_render_forward_backward_host(const float* h_faces, const float* h_textures, const float* h_grad_soft_colors,
@@ -536,9 +553,9 @@ static int forward_indexed_impl(const RenderParams& P, const float* vertices, co
 
 static int backward_indexed_impl(const RenderParams& P, const int* face_index, int index_shared, const float* textures, const float* soft_colors,
                                  const float* aggrs_info, float* grad_vertices, float* grad_textures, const float* grad_soft_colors,
-                                 int grad_is_pooled, int num_vertices, int zero_grads, void* workspace, cudaStream_t st) {
+                                 int grad_is_pooled, int num_vertices, int zero_grads, void* workspace, cudaStream_t st, bool batchsum = false) {
     if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)P.B * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
+        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)(batchsum ? 1 : P.B) * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
         if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)P.B * P.F * P.T * 3 * sizeof(float), st), "zero grad_textures");
     }
     KernelIO io;
@@ -548,7 +565,7 @@ static int backward_indexed_impl(const RenderParams& P, const int* face_index, i
     io.soft_colors = const_cast<float*>(soft_colors); io.aggrs = const_cast<float*>(aggrs_info);
     io.grad_colors = grad_soft_colors; io.grad_textures = grad_textures; io.grad_pooled = grad_is_pooled ? 1 : 0;
     io.grad_vertices = grad_vertices; io.face_index = face_index; io.index_batch_stride = index_shared ? 0 : (long long)P.F * 3;
-    io.num_vertices = num_vertices; io.grad_batch_stride_v = (long long)num_vertices * 3;
+    io.num_vertices = num_vertices; io.grad_batch_stride_v = batchsum ? 0 : (long long)num_vertices * 3;
     return run_render(P, io, true, st);
 }
 
@@ -583,6 +600,23 @@ int gendr_backward_render_indexed(const int* face_index, int index_shared, const
     GENDR_CUDA(dev.enter(grad_vertices), "selecting the device that owns `grad_vertices`");
     return backward_indexed_impl(P, face_index, index_shared, textures, soft_colors, aggrs_info, grad_vertices, grad_textures, grad_soft_colors,
                                  grad_is_pooled, num_vertices, zero_grads, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int gendr_backward_render_indexed_batchsum(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
+                                           const float* aggrs_info, float* grad_vertices_sum, float* grad_textures, const float* grad_soft_colors,
+                                           int grad_is_pooled, int batch, int num_vertices, int num_faces, int texture_size,
+                                           const gendr_render_params* params, int zero_grads, void* workspace, size_t workspace_bytes, void* stream) {
+    RenderParams P;
+    if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_indexed_batchsum");
+    if (batch == 0) return 0;
+    if (!face_index || !textures || !soft_colors || !aggrs_info || !grad_vertices_sum || !grad_soft_colors || !workspace || num_vertices < 1)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed_batchsum");
+    if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
+    if (int e = check_aa(P, grad_is_pooled ? grad_soft_colors : nullptr)) return e;
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(grad_vertices_sum), "selecting the device that owns `grad_vertices_sum`");
+    return backward_indexed_impl(P, face_index, index_shared, textures, soft_colors, aggrs_info, grad_vertices_sum, grad_textures, grad_soft_colors,
+                                 grad_is_pooled, num_vertices, zero_grads, workspace, reinterpret_cast<cudaStream_t>(stream), true);
 }
 
 // ---- fused 2x anti-aliasing on the face-vertex path ----------------------------------------
@@ -643,52 +677,55 @@ static int make_camera(CameraParams& C, const gendr_camera_params* u, int eyes_b
     memset(&C, 0, sizeof C);
     C.mode = u->mode; C.perspective = u->perspective ? 1 : 0; C.eye_stride = eyes_batched ? 3 : 0;
     for (int k = 0; k < 3; ++k) { C.at_or_dir[k] = u->at_or_direction[k]; C.up[k] = u->up[k]; }
-    // transform.py:20-22: torch.tan(torch.tensor(angle / 180 * math.pi, dtype=torch.float32))
-    C.width = tanf((float)((double)u->viewing_angle / 180. * 3.14159265358979323846));
-    C.inv_width = 1.f / C.width;
+    // transform.py:20-22: torch.tan(torch.tensor(angle / 180 * math.pi, dtype=torch.float32)) -- the tan() itself runs in the kernels
+    // (device libm, like torch's), the host only forms the fp32 angle
+    C.angle_rad = (float)((double)u->viewing_angle / 180. * 3.14159265358979323846);
     C.scale = u->viewing_scale;
     return 0;
 }
 static void make_light(LightParams& L, const gendr_light_params* u) {
     for (int k = 0; k < 3; ++k) {
         L.ambient[k] = u->intensity_ambient * u->color_ambient[k];
-        L.directional[k] = u->intensity_directional * u->color_directional[k];
+        L.color_dir[k] = u->color_directional[k];
         L.direction[k] = u->direction[k];
     }
+    L.intensity_dir = u->intensity_directional;
 }
 static unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 
-static int camera_forward_impl(const CameraParams& C, const float* vertices, const float* eyes, float* screen, int B, int V, cudaStream_t st) {
+static int camera_forward_impl(const CameraParams& C, const float* vertices, long long vstride, const float* eyes, float* screen, int B, int V,
+                               cudaStream_t st) {
     const long long n = (long long)B * V;
     if (n == 0) return 0;
-    camera_forward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, eyes, screen, B, V);
+    camera_forward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, vstride, eyes, screen, B, V);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "camera_forward_kernel launch");
     return 0;
 }
-static int camera_backward_impl(const CameraParams& C, const float* vertices, const float* eyes, const float* grad_screen, float* grad_vertices,
-                                int B, int V, cudaStream_t st) {
+static int camera_backward_impl(const CameraParams& C, const float* vertices, long long vstride, const float* eyes, const float* grad_screen,
+                                float* grad_vertices, int B, int V, cudaStream_t st) {
     const long long n = (long long)B * V;
     if (n == 0) return 0;
-    camera_backward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, eyes, grad_screen, grad_vertices, B, V);
+    camera_backward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, vstride, eyes, grad_screen, grad_vertices, B, V);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "camera_backward_kernel launch");
     return 0;
 }
-static int lighting_forward_impl(const LightParams& L, const float* vertices, const int* face_index, int index_shared, const float* textures,
-                                 float* lit, int B, int V, int F, int T, cudaStream_t st) {
+static int lighting_forward_impl(const LightParams& L, const float* vertices, long long vstride, const int* face_index, int index_shared,
+                                 const float* textures, float* lit, int B, int V, int F, int T, cudaStream_t st) {
     const long long n = (long long)B * F;
     if (n == 0) return 0;
-    lighting_forward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, face_index, index_shared ? 0 : (long long)F * 3, textures, lit, B, V, F, T);
+    lighting_forward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, vstride, face_index, index_shared ? 0 : (long long)F * 3, textures, lit, B, V, F, T);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "lighting_forward_kernel launch");
     return 0;
 }
-static int lighting_backward_impl(const LightParams& L, const float* vertices, const int* face_index, int index_shared, const float* textures,
-                                  const float* grad_lit, float* grad_textures, float* grad_vertices, int B, int V, int F, int T, cudaStream_t st) {
+static int lighting_backward_impl(const LightParams& L, const float* vertices, long long vstride, const int* face_index, int index_shared,
+                                  const float* textures, const float* grad_lit, float* grad_textures, float* grad_vertices, int B, int V, int F, int T,
+                                  cudaStream_t st) {
     const long long n = (long long)B * F;
     if (n == 0) return 0;
-    lighting_backward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, face_index, index_shared ? 0 : (long long)F * 3, textures, grad_lit,
+    lighting_backward_kernel<<<blocks_for(n), 256, 0, st>>>(L, vertices, vstride, face_index, index_shared ? 0 : (long long)F * 3, textures, grad_lit,
                                                             grad_textures, grad_vertices, B, V, F, T);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "lighting_backward_kernel launch");
@@ -703,7 +740,7 @@ int gendr_camera_forward(const float* vertices, const float* eyes, int eyes_batc
     if (!vertices || !eyes || !screen_vertices) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_forward");
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    return camera_forward_impl(C, vertices, eyes, screen_vertices, batch, num_vertices, reinterpret_cast<cudaStream_t>(stream));
+    return camera_forward_impl(C, vertices, (long long)num_vertices * 3, eyes, screen_vertices, batch, num_vertices, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_batched, const float* grad_screen_vertices, float* grad_vertices,
@@ -714,7 +751,8 @@ int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_bat
     if (!vertices || !eyes || !grad_screen_vertices || !grad_vertices) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_backward");
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    return camera_backward_impl(C, vertices, eyes, grad_screen_vertices, grad_vertices, batch, num_vertices, reinterpret_cast<cudaStream_t>(stream));
+    return camera_backward_impl(C, vertices, (long long)num_vertices * 3, eyes, grad_screen_vertices, grad_vertices, batch, num_vertices,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gendr_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, float* lit_textures, int batch,
@@ -726,7 +764,7 @@ int gendr_lighting_forward(const float* vertices, const int* face_index, int ind
     make_light(L, light);
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    return lighting_forward_impl(L, vertices, face_index, index_shared, textures, lit_textures, batch, num_vertices, num_faces, texture_size,
+    return lighting_forward_impl(L, vertices, (long long)num_vertices * 3, face_index, index_shared, textures, lit_textures, batch, num_vertices, num_faces, texture_size,
                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -740,7 +778,7 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
     make_light(L, light);
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    return lighting_backward_impl(L, vertices, face_index, index_shared, textures, grad_lit_textures, grad_textures, grad_vertices, batch,
+    return lighting_backward_impl(L, vertices, (long long)num_vertices * 3, face_index, index_shared, textures, grad_lit_textures, grad_textures, grad_vertices, batch,
                                   num_vertices, num_faces, texture_size, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -763,7 +801,7 @@ size_t gendr_scene_workspace_bytes(int batch, int num_vertices, int num_faces, i
            2 * al256((size_t)batch * num_faces * texture_size * 12) + 256;
 }
 
-int gendr_scene_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
+int gendr_scene_forward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
                         const gendr_camera_params* camera, const gendr_light_params* light, float* aggrs_info, float* soft_colors,
                         float* pooled_colors, int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
                         void* workspace, size_t workspace_bytes, void* stream) {
@@ -782,18 +820,19 @@ int gendr_scene_forward(const float* vertices, const int* face_index, int index_
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const SceneWs w = scene_ws(workspace, batch, num_vertices, num_faces, texture_size);
-    if (int e = camera_forward_impl(C, vertices, eyes, w.screen, batch, num_vertices, st)) return e;
+    const long long vstride = vertices_shared ? 0 : (long long)num_vertices * 3;
+    if (int e = camera_forward_impl(C, vertices, vstride, eyes, w.screen, batch, num_vertices, st)) return e;
     const float* tex = textures;
     if (light) {
         LightParams L;
         make_light(L, light);
-        if (int e = lighting_forward_impl(L, vertices, face_index, index_shared, textures, w.lit, batch, num_vertices, num_faces, texture_size, st)) return e;
+        if (int e = lighting_forward_impl(L, vertices, vstride, face_index, index_shared, textures, w.lit, batch, num_vertices, num_faces, texture_size, st)) return e;
         tex = w.lit;
     }
     return forward_indexed_impl(P, w.screen, face_index, index_shared, tex, aggrs_info, soft_colors, pooled_colors, num_vertices, w.render, st);
 }
 
-int gendr_scene_backward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
+int gendr_scene_backward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
                          const gendr_camera_params* camera, const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
                          const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures, int batch,
                          int num_vertices, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
@@ -820,11 +859,13 @@ int gendr_scene_backward(const float* vertices, const int* face_index, int index
     if (g_tex) GENDR_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)batch * num_faces * texture_size * 12, st), "zero texture gradient");
     if (int e = backward_indexed_impl(P, face_index, index_shared, light ? w.lit : textures, soft_colors, aggrs_info, w.grad_screen, g_tex,
                                       grad_soft_colors, grad_is_pooled, num_vertices, 0, w.render, st)) return e;
-    if (int e = camera_backward_impl(C, vertices, eyes, w.grad_screen, grad_vertices, batch, num_vertices, st)) return e;
+    const long long vstride = vertices_shared ? 0 : (long long)num_vertices * 3;
+    if (vertices_shared) GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)num_vertices * 12, st), "zero the batch-summed vertex gradient");
+    if (int e = camera_backward_impl(C, vertices, vstride, eyes, w.grad_screen, grad_vertices, batch, num_vertices, st)) return e;
     if (light) {
         LightParams L;
         make_light(L, light);
-        if (int e = lighting_backward_impl(L, vertices, face_index, index_shared, textures, w.grad_lit, grad_textures, grad_vertices, batch,
+        if (int e = lighting_backward_impl(L, vertices, vstride, face_index, index_shared, textures, w.grad_lit, grad_textures, grad_vertices, batch,
                                            num_vertices, num_faces, texture_size, st)) return e;
     }
     return 0;

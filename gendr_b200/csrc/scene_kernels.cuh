@@ -11,9 +11,19 @@
 // camera basis is recomputed per thread from the eye (about 40 flops) instead of being staged through memory by a
 // separate launch: these kernels are launch-latency bound, not bandwidth bound.
 //
-// Arithmetic: plain fp32, same formulas and the same clamps (F.normalize eps 1e-5 / 1e-6, relu) as the reference.  The
-// reference evaluates them with torch reductions and a cuBLAS batched matmul whose summation order is not specified, so
-// parity here is "a few ulp" (tests: rtol 2e-6 on screen-space vertices and lit textures), not bit-exact.
+// Arithmetic: the FORWARD kernels reproduce, operation for operation, what torch 2.x + cuBLAS compute for the reference's Python
+// on a B200 -- identified by dumping every intermediate on the box (tools/gpu_scene_probe.py) and matching candidate orderings
+// offline (tools/scene_probe_analyze.py: each rule below reproduces 100 % of 10^4..10^5 samples bit for bit):
+//   torch.norm / torch.sum over a 3-vector   (t0 + t2) + t1 with individually rounded terms (thread 0 of the 2-thread reduction
+//                                            owns elements 0 and 2, thread 1 element 1)
+//   F.normalize                              IEEE division by max(norm, eps), per component
+//   torch.cross                              fma(a1, b2, -(a2*b1)) and cyclic
+//   torch.matmul(v - eye, R^T) (cuBLAS)      fma(d2, r2, fma(d1, r1, d0*r0))
+//   perspective                              (x / z) / width, two IEEE divisions; width = tan() evaluated by the DEVICE libm
+//   lighting                                 ambient + intensity * (colour * relu(cos)), every torch op rounded on its own
+// Why it matters: the rasterizer's geometric stage amplifies 1-ulp differences of screen-space vertices into 1e-4-level image
+// differences on sliver faces, so end-to-end parity with the reference package needs bit-identical vertices.
+// The backward kernels are plain fp32 (gradients are sums; parity there is a few ulp).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -26,29 +36,36 @@ struct CameraParams {
     int   eye_stride;      // 3 = eyes [B,3], 0 = one eye shared by the batch
     float at_or_dir[3];    // look_at: the point looked at; look: the viewing direction
     float up[3];
-    float inv_width;       // 1 / tan(viewing_angle)   (transform.py:22-27 divides by z, then by width)
-    float width;           // tanf(viewing_angle in radians), fp32 like the reference
+    float angle_rad;       // (float)(viewing_angle / 180 * pi): transform.py:20 builds this fp32 tensor, torch.tan() runs on the device
     float scale;           // orthogonal scale
 };
 
 struct LightParams {
-    float ambient[3];      // intensity_ambient * color_ambient
-    float directional[3];  // intensity_directionals * color_directionals
+    float ambient[3];      // intensity_ambient * color_ambient (fp32 product, lighting.py:22)
+    float intensity_dir;   // intensity_directionals
+    float color_dir[3];    // color_directionals
     float direction[3];
 };
 
 struct f3 { float x, y, z; };
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }      // backward passes only
+// torch.sum over a 3-vector of products: (t0 + t2) + t1, every term rounded on its own
+__device__ __forceinline__ float sum3_torch(float t0, float t1, float t2) { return __fadd_rn(__fadd_rn(t0, t2), t1); }
+// row of cuBLAS' [.,3] x [3,3] product: fma(d2, r2, fma(d1, r1, d0*r0))
+__device__ __forceinline__ float dot3_gemm(f3 d, f3 r) { return __fmaf_rn(d.z, r.z, __fmaf_rn(d.y, r.y, __fmul_rn(d.x, r.x))); }
+// torch.cross: fma(a1, b2, -(a2*b1)) and cyclic
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return mk3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
 __device__ __forceinline__ f3 scale3(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
-// F.normalize(v, eps): v / max(||v||_2, eps)
+// F.normalize(v, eps): v / max(||v||_2, eps), torch.norm = sqrt((x^2 + z^2) + y^2)
 __device__ __forceinline__ f3 normalize3(f3 a, float eps, float* norm_out = nullptr) {
-    const float n = sqrtf(dot3(a, a));
+    const float n = __fsqrt_rn(sum3_torch(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y), __fmul_rn(a.z, a.z)));
     if (norm_out) *norm_out = n;
     const float d = fmaxf(n, eps);
-    return mk3(a.x / d, a.y / d, a.z / d);
+    return mk3(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d));
 }
 __device__ __forceinline__ f3 load3(const float* p) { return mk3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
@@ -65,43 +82,56 @@ __device__ __forceinline__ CameraBasis camera_basis(const CameraParams& C, const
 }
 
 // ---- forward: world -> screen space, one thread per vertex -----------------------------------------------------
+// vstride: batch stride of `vertices` in floats -- V*3, or 0 when ONE mesh [V,3] is shared by the whole batch (the views differ
+// only by their eyes: vertices.repeat(B,1,1) of experiments/opt_shape.py:86 without materialising the copies)
 __global__ void __launch_bounds__(256) camera_forward_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ vertices,
-                                                             const float* __restrict__ eyes, float* __restrict__ screen, int B, int V) {
+                                                             long long vstride, const float* __restrict__ eyes, float* __restrict__ screen,
+                                                             int B, int V) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * V) return;
     const int b = (int)(i / V);
+    const long long v = i - (long long)b * V;
     const CameraBasis K = camera_basis(C, eyes, b);
-    const f3 d = sub3(load3(vertices + i * 3), K.eye);               // look_at.py:64 (only_rotate = False)
-    const float xc = dot3(d, K.x), yc = dot3(d, K.y), zc = dot3(d, K.z);   // look_at.py:66: matmul(v, r^T)
+    const f3 d = sub3(load3(vertices + b * vstride + v * 3), K.eye);               // look_at.py:64 (only_rotate = False)
+    const float xc = dot3_gemm(d, K.x), yc = dot3_gemm(d, K.y), zc = dot3_gemm(d, K.z);   // look_at.py:66: matmul(v, r^T)
     float xs, ys;
-    if (C.perspective) { xs = xc / zc / C.width; ys = yc / zc / C.width; }  // transform.py:25-27
-    else { xs = xc * C.scale; ys = yc * C.scale; }                          // transform.py:41-42
+    if (C.perspective) {                                                    // transform.py:20-27
+        const float width = tanf(C.angle_rad);
+        xs = __fdiv_rn(__fdiv_rn(xc, zc), width); ys = __fdiv_rn(__fdiv_rn(yc, zc), width);
+    } else { xs = __fmul_rn(xc, C.scale); ys = __fmul_rn(yc, C.scale); }    // transform.py:41-42
     screen[i * 3 + 0] = xs; screen[i * 3 + 1] = ys; screen[i * 3 + 2] = zc;
 }
 
-// ---- backward: grad_screen [B,V,3] -> grad_vertices [B,V,3] (plain store: every thread owns its vertex) --------
+// ---- backward: grad_screen [B,V,3] -> grad_vertices [B,V,3] (plain store: every thread owns its vertex), or, for a mesh shared
+// by the batch (vstride == 0), red.add into the batch-summed grad_vertices [V,3] (zero-filled by the caller) --------------------
 __global__ void __launch_bounds__(256) camera_backward_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ vertices,
-                                                              const float* __restrict__ eyes, const float* __restrict__ grad_screen,
-                                                              float* __restrict__ grad_vertices, int B, int V) {
+                                                              long long vstride, const float* __restrict__ eyes,
+                                                              const float* __restrict__ grad_screen, float* __restrict__ grad_vertices, int B,
+                                                              int V) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * V) return;
     const int b = (int)(i / V);
+    const long long v = i - (long long)b * V;
     const CameraBasis K = camera_basis(C, eyes, b);
     const f3 g = load3(grad_screen + i * 3);
     float gxc, gyc, gzc;
     if (C.perspective) {
-        const f3 d = sub3(load3(vertices + i * 3), K.eye);
-        const float xc = dot3(d, K.x), yc = dot3(d, K.y), zc = dot3(d, K.z);
-        const float r = 1.f / (zc * C.width);                        // d(xs)/d(xc)
+        const f3 d = sub3(load3(vertices + b * vstride + v * 3), K.eye);
+        const float xc = dot3_gemm(d, K.x), yc = dot3_gemm(d, K.y), zc = dot3_gemm(d, K.z);
+        const float r = 1.f / (zc * tanf(C.angle_rad));              // d(xs)/d(xc)
         gxc = g.x * r; gyc = g.y * r;
         gzc = g.z - (g.x * xc + g.y * yc) * r / zc;                  // xs = xc / zc / width  =>  d(xs)/d(zc) = -xs / zc
     } else {
         gxc = g.x * C.scale; gyc = g.y * C.scale; gzc = g.z;
     }
     // v_cam = R (v - eye)  =>  grad_v = R^T grad_cam
-    grad_vertices[i * 3 + 0] = gxc * K.x.x + gyc * K.y.x + gzc * K.z.x;
-    grad_vertices[i * 3 + 1] = gxc * K.x.y + gyc * K.y.y + gzc * K.z.y;
-    grad_vertices[i * 3 + 2] = gxc * K.x.z + gyc * K.y.z + gzc * K.z.z;
+    const float gx = gxc * K.x.x + gyc * K.y.x + gzc * K.z.x, gy = gxc * K.x.y + gyc * K.y.y + gzc * K.z.y,
+                gz = gxc * K.x.z + gyc * K.y.z + gzc * K.z.z;
+    if (vstride != 0) {
+        grad_vertices[i * 3 + 0] = gx; grad_vertices[i * 3 + 1] = gy; grad_vertices[i * 3 + 2] = gz;
+    } else {
+        atomicAdd(grad_vertices + v * 3 + 0, gx); atomicAdd(grad_vertices + v * 3 + 1, gy); atomicAdd(grad_vertices + v * 3 + 2, gz);
+    }
 }
 
 // ---- lighting of one face (surface textures) ---------------------------------------------------------------------
@@ -110,10 +140,11 @@ __device__ __forceinline__ void face_light(const LightParams& L, f3 v0, f3 v1, f
                                            float* norm_out = nullptr, float* cos_out = nullptr) {
     float norm;
     const f3 n = normalize3(cross3(sub3(v2, v1), sub3(v0, v1)), 1e-6f, &norm);     // mesh.py:105-108
-    const float c = n.x * L.direction[0] + n.y * L.direction[1] + n.z * L.direction[2];
+    const float c = sum3_torch(__fmul_rn(n.x, L.direction[0]), __fmul_rn(n.y, L.direction[1]), __fmul_rn(n.z, L.direction[2]));
     const float cosine = fmaxf(c, 0.f);                                            // functional/lighting.py:46 (relu)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) light[k] = L.ambient[k] + L.directional[k] * cosine;   // :22 and :47
+    for (int k = 0; k < 3; ++k)                                                    // :22 and :47, each torch op rounded on its own
+        light[k] = __fadd_rn(L.ambient[k], __fmul_rn(L.intensity_dir, __fmul_rn(L.color_dir[k], cosine)));
     if (n_out) *n_out = n;
     if (norm_out) *norm_out = norm;
     if (cos_out) *cos_out = c;
@@ -123,14 +154,14 @@ __device__ __forceinline__ int clamp_index(int vi, int V) { return min(max(vi, 0
 
 // forward: lit_textures[b,f,t,:] = textures[b,f,t,:] * light(b,f)      (lighting.py:58)
 __global__ void __launch_bounds__(256) lighting_forward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ vertices,
-                                                               const int* __restrict__ face_index, long long index_batch_stride,
+                                                               long long vstride, const int* __restrict__ face_index, long long index_batch_stride,
                                                                const float* __restrict__ textures, float* __restrict__ lit, int B, int V,
                                                                int F, int T) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * F) return;
     const long long b = i / F, f = i - b * F;
     const int* idx = face_index + b * index_batch_stride + f * 3;
-    const float* vb = vertices + b * V * 3;
+    const float* vb = vertices + b * vstride;
     const f3 v0 = load3(vb + (size_t)clamp_index(__ldg(idx + 0), V) * 3), v1 = load3(vb + (size_t)clamp_index(__ldg(idx + 1), V) * 3),
              v2 = load3(vb + (size_t)clamp_index(__ldg(idx + 2), V) * 3);
     float light[3];
@@ -139,13 +170,13 @@ __global__ void __launch_bounds__(256) lighting_forward_kernel(const __grid_cons
     float* dst = lit + i * T * 3;
     for (int t = 0; t < T; ++t)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) dst[t * 3 + k] = __ldg(src + t * 3 + k) * light[k];
+        for (int k = 0; k < 3; ++k) dst[t * 3 + k] = __fmul_rn(__ldg(src + t * 3 + k), light[k]);
 }
 
 // backward: grad_lit [B,F,T,3] -> grad_textures [B,F,T,3] (store; may be null) and, through the surface normal, atomic
 // adds into grad_vertices [B,V,3] (which already holds the camera path's gradient; may be null).
 __global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ vertices,
-                                                                const int* __restrict__ face_index, long long index_batch_stride,
+                                                                long long vstride, const int* __restrict__ face_index, long long index_batch_stride,
                                                                 const float* __restrict__ textures, const float* __restrict__ grad_lit,
                                                                 float* __restrict__ grad_textures, float* __restrict__ grad_vertices,
                                                                 int B, int V, int F, int T) {
@@ -154,7 +185,7 @@ __global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_con
     const long long b = i / F, f = i - b * F;
     const int* idx = face_index + b * index_batch_stride + f * 3;
     const int i0 = clamp_index(__ldg(idx + 0), V), i1 = clamp_index(__ldg(idx + 1), V), i2 = clamp_index(__ldg(idx + 2), V);
-    const float* vb = vertices + b * V * 3;
+    const float* vb = vertices + b * vstride;
     const f3 v0 = load3(vb + (size_t)i0 * 3), v1 = load3(vb + (size_t)i1 * 3), v2 = load3(vb + (size_t)i2 * 3);
     float light[3], norm, c;
     f3 n;
@@ -170,7 +201,7 @@ __global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_con
             if (grad_textures) grad_textures[i * T * 3 + t * 3 + k] = g * light[k];
         }
     if (!grad_vertices || !(c > 0.f)) return;                        // relu: no gradient at or below 0
-    const float gcos = L.directional[0] * G[0] + L.directional[1] * G[1] + L.directional[2] * G[2];
+    const float gcos = L.intensity_dir * (L.color_dir[0] * G[0] + L.color_dir[1] * G[1] + L.color_dir[2] * G[2]);
     if (gcos == 0.f) return;
     const f3 gn = mk3(gcos * L.direction[0], gcos * L.direction[1], gcos * L.direction[2]);
     f3 gc;                                                            // gradient w.r.t. the un-normalised cross product
@@ -178,7 +209,7 @@ __global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_con
     else gc = scale3(gn, 1e6f);                                       // clamped norm: n = c / eps
     const f3 a = sub3(v2, v1), e = sub3(v0, v1);                      // c = a x e
     const f3 ga = cross3(e, gc), ge = cross3(gc, a);
-    float* gv = grad_vertices + b * V * 3;
+    float* gv = grad_vertices + b * vstride;       // shared mesh (vstride == 0): straight into the batch-summed [V,3]
     atomicAdd(gv + (size_t)i2 * 3 + 0, ga.x); atomicAdd(gv + (size_t)i2 * 3 + 1, ga.y); atomicAdd(gv + (size_t)i2 * 3 + 2, ga.z);
     atomicAdd(gv + (size_t)i0 * 3 + 0, ge.x); atomicAdd(gv + (size_t)i0 * 3 + 1, ge.y); atomicAdd(gv + (size_t)i0 * 3 + 2, ge.z);
     atomicAdd(gv + (size_t)i1 * 3 + 0, -(ga.x + ge.x)); atomicAdd(gv + (size_t)i1 * 3 + 1, -(ga.y + ge.y));

@@ -81,6 +81,19 @@ def backward_render_raw(faces, textures, soft_colors, aggrs_info, grad_faces, gr
         int(workspace_valid), int(zero_grads), workspace.data_ptr(), workspace.numel(), _stream(faces.device)))
 
 
+def backward_render_batchsum_raw(faces, textures, soft_colors, aggrs_info, grad_faces_sum, grad_textures, grad_soft_colors, params, workspace,
+                                 workspace_valid, zero_grads):
+    """Backward pass accumulating the gradient of a mesh shared by the batch straight into grad_faces_sum [F,9]
+    (gendr_backward_render_batchsum; SURVEY 8(e) "fusion with the collective")."""
+    lib = _lib.load()
+    B, F = int(faces.shape[0]), int(faces.shape[1])
+    T = int(textures.shape[2])
+    _lib.check(lib.gendr_backward_render_batchsum(
+        faces.data_ptr(), textures.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_faces_sum.data_ptr(),
+        grad_textures.data_ptr() if grad_textures is not None else None, grad_soft_colors.data_ptr(), B, F, T, params,
+        int(workspace_valid), int(zero_grads), workspace.data_ptr(), workspace.numel(), _stream(faces.device)))
+
+
 def forward_render_aa_raw(faces, textures, aggrs_info, soft_colors, pooled_colors, params, workspace):
     lib = _lib.load()
     B, F = int(faces.shape[0]), int(faces.shape[1])

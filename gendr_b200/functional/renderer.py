@@ -232,7 +232,16 @@ class GenDRSceneFunction(Function):
             raise TypeError('GenDR only supports CUDA Tensors.')
         verts = vertices.detach().to(torch.float32).contiguous()
         dev = verts.device
-        B, V = verts.shape[:2]
+        eyes = eyes.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eyes_batched = eyes.ndimension() == 2
+        # vertices [V,3]: ONE mesh seen from every eye (the shared-mesh pattern of experiments/opt_shape.py:86 without
+        # vertices.repeat(batch, 1, 1)); the gradient comes back batch-summed as [V,3]
+        verts_shared = verts.ndimension() == 2
+        if verts_shared:
+            V = verts.shape[0]
+            B = eyes.shape[0] if eyes_batched else int(textures.shape[0])
+        else:
+            B, V = verts.shape[:2]
         check_face_indices(faces, V)
         index = faces.detach().to(device=dev, dtype=torch.int32).contiguous()
         shared = index.ndimension() == 2
@@ -240,8 +249,6 @@ class GenDRSceneFunction(Function):
         tex = textures.detach().to(device=dev, dtype=torch.float32).contiguous()
         tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
         T = int(tex.shape[2])
-        eyes = eyes.detach().to(device=dev, dtype=torch.float32).contiguous()
-        eyes_batched = eyes.ndimension() == 2
         if eyes_batched and eyes.shape[0] != B:
             raise ValueError('eyes must be [3] or [batch, 3]')
         S = int(params.image_size)
@@ -252,17 +259,17 @@ class GenDRSceneFunction(Function):
         workspace = torch.empty(lib.gendr_scene_workspace_bytes(B, V, F, T), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _ext._lib.check(lib.gendr_scene_forward(
-                verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
+                verts.data_ptr(), int(verts_shared), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
                 aggrs_info.data_ptr(), soft_colors.data_ptr(), pooled.data_ptr() if anti_aliasing else None, B, V, F, T, params,
                 workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(dev).cuda_stream))
-        ctx.cfg = (camera, light, params, bool(anti_aliasing), (B, V, F, T, shared, eyes_batched), (vertices.shape, textures.shape))
+        ctx.cfg = (camera, light, params, bool(anti_aliasing), (B, V, F, T, shared, eyes_batched, verts_shared), (vertices.shape, textures.shape))
         ctx.save_for_backward(verts, index, tex, eyes, soft_colors, aggrs_info, workspace)
         return pooled if anti_aliasing else soft_colors
 
     @staticmethod
     def backward(ctx, grad_images):
         verts, index, tex, eyes, soft_colors, aggrs_info, workspace = ctx.saved_tensors
-        camera, light, params, aa, (B, V, F, T, shared, eyes_batched), (vshape, tshape) = ctx.cfg
+        camera, light, params, aa, (B, V, F, T, shared, eyes_batched, verts_shared), (vshape, tshape) = ctx.cfg
         grad_images = grad_images.to(torch.float32).contiguous()
         want_tex = ctx.needs_input_grad[2]
         grad_vertices = torch.empty_like(verts)
@@ -270,7 +277,7 @@ class GenDRSceneFunction(Function):
         lib = _ext._lib.load()
         with torch.cuda.device(verts.device):
             _ext._lib.check(lib.gendr_scene_backward(
-                verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
+                verts.data_ptr(), int(verts_shared), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
                 soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_images.data_ptr(), int(aa), grad_vertices.data_ptr(),
                 grad_tex.data_ptr() if want_tex else None, B, V, F, T, params, workspace.data_ptr(), workspace.numel(),
                 torch.cuda.current_stream(verts.device).cuda_stream))
@@ -284,6 +291,9 @@ def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, im
                  near=1, far=100, double_side=True, texture_type='surface', anti_aliasing=False):
     """World-space mesh (vertices [B,V,3], faces [B,F,3] | [F,3], surface textures [B,F,T,3]) seen from `eyes` ([B,3] | [3])
     -> RGBA images: lighting(mesh); transform(mesh); renderer(mesh) of the reference's scripts in one fused node.
+    vertices [V,3] (2-D): ONE mesh shared by all views (experiments/opt_shape.py:86 renders vertices.repeat(batch, 1, 1)); the
+    copies are never materialised and the vertex gradient arrives batch-summed, [V,3] -- the buffer a data-parallel rank hands
+    to its single all-reduce (gendr_b200.parallel.allreduce_shared_vertex_grads).
     camera: dict for make_camera_params (mode, perspective, viewing_angle, viewing_scale, at, up, direction);
     lighting: dict for make_light_params, or None for no lighting step."""
     assert dist_scale >= 0, dist_scale

@@ -28,8 +28,10 @@ def shard_batch(tensor, rank=None, world_size=None):
 
 def allreduce_shared_face_grads(grad_faces, group=None):
     """grad_faces [b_local, F, 3, 3] -> gradient w.r.t. the batch-shared face vertices [F, 3, 3], summed over the local
-    slice and all-reduced across ranks (in place on the local sum; async on the current stream under NCCL)."""
-    total = grad_faces.sum(dim=0)
+    slice and all-reduced across ranks (in place on the local sum; async on the current stream under NCCL).
+    An already batch-summed buffer ([F, 3, 3] / [F, 9], what gendr_backward_render_batchsum accumulates inside the backward
+    kernel) goes to the all-reduce as it is: no intermediate [b_local, F, 3, 3] tensor and no reduction kernel."""
+    total = grad_faces.sum(dim=0) if grad_faces.ndimension() == 4 else grad_faces
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total
@@ -39,7 +41,7 @@ def allreduce_shared_vertex_grads(grad_vertices, group=None):
     """grad_vertices [b_local, V, 3] (what the indexed / scene paths return) -> gradient w.r.t. the batch-shared vertices
     [V, 3]: local batch sum + ONE all-reduce(SUM).  The payload is 6x smaller than the per-face form (51 KB instead of 295 KB at
     V = 4225 / F = 8192)."""
-    total = grad_vertices.sum(dim=0)
+    total = grad_vertices.sum(dim=0) if grad_vertices.ndimension() == 3 else grad_vertices      # [V,3]: summed by the kernels
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     return total

@@ -74,6 +74,22 @@ int gendr_backward_render(const float* faces, const float* textures, const float
                           const gendr_render_params* params, int workspace_valid, int zero_grads,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batch-summed gradient (SURVEY.md 8(e) "fusion with the collective").  When one mesh is shared by the whole batch
+ * (vertices.repeat(batch, 1, 1), /root/reference/experiments/opt_shape.py:86) the gradient the optimiser needs is the SUM over the
+ * batch -- which the reference gets from autograd's backward of `repeat` after writing [B,F,3,3].  These variants accumulate
+ * straight into ONE [F,3,3] (or, indexed, [V,3]) buffer, so a data-parallel rank can hand that buffer to a single all-reduce
+ * without an intermediate [B,F,3,3] tensor or a reduction kernel.  Everything else as in gendr_backward_render(_indexed). */
+int gendr_backward_render_batchsum(const float* faces, const float* textures, const float* soft_colors,
+                                   const float* aggrs_info, float* grad_faces_sum, float* grad_textures,
+                                   const float* grad_soft_colors, int batch, int num_faces, int texture_size,
+                                   const gendr_render_params* params, int workspace_valid, int zero_grads,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+int gendr_backward_render_indexed_batchsum(const int* face_index, int index_shared, const float* textures, const float* soft_colors,
+                                           const float* aggrs_info, float* grad_vertices_sum, float* grad_textures,
+                                           const float* grad_soft_colors, int grad_is_pooled, int batch, int num_vertices,
+                                           int num_faces, int texture_size, const gendr_render_params* params, int zero_grads,
+                                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Indexed-mesh variants: fuse the reference's `vertices[faces]` gather
  * (gendr/functional/face_vertices.py:9-27, called from gendr/mesh.py:102) into the face preprocessing and its backward
  * (a scatter-add into the vertex gradient) into the backward kernel, so the [B,F,3,3] face-vertex tensor and its
@@ -144,14 +160,18 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
  * Backward: render backward (scatter-adds into the screen-space vertex gradient and the lit-texture gradient held in the
  * workspace), camera backward, lighting backward -> grad_vertices [B,V,3] w.r.t. the WORLD-space vertices and
  * grad_textures [B,F,T,3] w.r.t. the UNLIT textures (may be NULL).  light may be NULL (no lighting step).
- * pooled_colors / grad_is_pooled as in gendr_forward_render_aa. */
+ * pooled_colors / grad_is_pooled as in gendr_forward_render_aa.
+ * vertices_shared != 0: ONE world-space mesh `vertices` [V,3] seen from `batch` eyes (the shared-mesh pattern of
+ * experiments/opt_shape.py:86 without materialising vertices.repeat(batch,1,1)); gendr_scene_backward then returns the
+ * batch-SUMMED gradient grad_vertices [V,3] (camera path: red.add per view; normals' path: added once per view), which is what
+ * autograd's backward of `repeat` would produce -- ready for one all-reduce across data-parallel ranks. */
 size_t gendr_scene_workspace_bytes(int batch, int num_vertices, int num_faces, int texture_size);
-int gendr_scene_forward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+int gendr_scene_forward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures,
                         const float* eyes, int eyes_batched, const gendr_camera_params* camera,
                         const gendr_light_params* light, float* aggrs_info, float* soft_colors, float* pooled_colors,
                         int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
                         void* workspace, size_t workspace_bytes, void* stream);
-int gendr_scene_backward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+int gendr_scene_backward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures,
                          const float* eyes, int eyes_batched, const gendr_camera_params* camera,
                          const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
                          const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures,

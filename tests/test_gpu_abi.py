@@ -115,3 +115,48 @@ def test_fused_paths_validate_face_indices():
         gd.functional.render_scene(v, neg.to(dev), tex, [0., 0., -3.], image_size=16)
     with pytest.raises(ValueError):
         gd.functional.render_scene(v, faces.to(dev), tex, torch.tensor([0., 0., -3.], device=dev, requires_grad=True), image_size=16)
+
+
+def test_batch_summed_backward_equals_sum_of_per_item_gradients():
+    """gendr_backward_render_batchsum / _indexed_batchsum accumulate the gradient of a mesh shared by the batch into ONE [F,9] /
+    [V,3] buffer == the batch sum of what gendr_backward_render(_indexed) writes per item (SURVEY 8(e) "fusion with the collective")."""
+    dev = _dev()
+    lib = _lib.load()
+    fv, ft, kw = scenes.config_c2(batch=6, image_size=96)
+    B, F = fv.shape[:2]
+    S = 96
+    for dist_id, tcn_id, p in ((6, 2, 0.0), (8, 6, 2.0)):          # sparse (pixel-stationary) and dense (face-stationary) backward kernels
+        params = ext.make_params(S, dist_id, 0.01, False, 0., 0., 1e4, tcn_id, p, 1, 1e-3, 1e-3, 1., 100., False, 0)
+        faces, tex = fv.to(dev).view(B, F, 9).contiguous(), ft.to(dev).contiguous()
+        g = torch.randn(B, 4, S, S, generator=torch.Generator().manual_seed(4)).to(dev)
+        colors, aggrs = torch.empty(B, 4, S, S, device=dev), torch.empty(B, 2, S, S, device=dev)
+        ws = ext.workspace_for(faces)
+        ext.forward_render_raw(faces, tex, None, aggrs, colors, params, False, ws)
+        gf, gt = torch.empty(B, F, 9, device=dev), torch.empty(B, F, 1, 3, device=dev)
+        ext.backward_render_raw(faces, tex, colors, aggrs, gf, gt, g, params, ws, True, True)
+        gsum, gt2 = torch.full((F, 9), float('nan'), device=dev), torch.empty(B, F, 1, 3, device=dev)
+        ext.backward_render_batchsum_raw(faces, tex, colors, aggrs, gsum, gt2, g, params, ws, True, True)
+        want = gf.double().sum(0)
+        assert float((gsum.double() - want).abs().max()) <= 2e-5 * float(want.abs().max()), (dist_id, tcn_id)
+        assert float((gt2 - gt).abs().max()) <= 2e-5 * float(gt.abs().max())
+    # indexed: [V,3]
+    import gendr_b200 as gd
+    verts, index = scenes.icosphere(3)
+    v = gd.LookAt(viewing_angle=15).transform((verts * 0.5)[None].repeat(4, 1, 1)).to(dev).contiguous()
+    idx = index.to(dev).int().contiguous()
+    tex = torch.rand(4, index.shape[0], 1, 3, generator=torch.Generator().manual_seed(1)).to(dev)
+    V, F = v.shape[1], idx.shape[0]
+    params = ext.make_params(64, 6, 0.02, False, 0., 0., 1e4, 2, 0., 1, 1e-3, 1e-3, 1., 100., False, 0)
+    colors, aggrs = torch.empty(4, 4, 64, 64, device=dev), torch.empty(4, 2, 64, 64, device=dev)
+    ws = torch.empty(lib.gendr_workspace_bytes(4, F), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.gendr_forward_render_indexed(v.data_ptr(), idx.data_ptr(), 1, tex.data_ptr(), aggrs.data_ptr(), colors.data_ptr(), None, 4, V, F, 1,
+                                                C.byref(params), ws.data_ptr(), ws.numel(), st))
+    g = torch.randn(4, 4, 64, 64, generator=torch.Generator().manual_seed(5)).to(dev)
+    gv, gvs = torch.empty(4, V, 3, device=dev), torch.empty(V, 3, device=dev)
+    _lib.check(lib.gendr_backward_render_indexed(idx.data_ptr(), 1, tex.data_ptr(), colors.data_ptr(), aggrs.data_ptr(), gv.data_ptr(), None, g.data_ptr(), 0,
+                                                 4, V, F, 1, C.byref(params), 1, ws.data_ptr(), ws.numel(), st))
+    _lib.check(lib.gendr_backward_render_indexed_batchsum(idx.data_ptr(), 1, tex.data_ptr(), colors.data_ptr(), aggrs.data_ptr(), gvs.data_ptr(), None,
+                                                          g.data_ptr(), 0, 4, V, F, 1, C.byref(params), 1, ws.data_ptr(), ws.numel(), st))
+    want = gv.double().sum(0)
+    assert float((gvs.double() - want).abs().max()) <= 2e-5 * float(want.abs().max())

@@ -52,6 +52,9 @@ def _worker(rank, world, port, out_dir):
     f = oracle.forward(parallel.shard_batch(fv).numpy(), parallel.shard_batch(ft).numpy(), p)
     gf, _ = oracle.backward(f, parallel.shard_batch(g).numpy(), p)
     shared = parallel.allreduce_shared_face_grads(torch.from_numpy(gf).view(hi - lo, -1, 3, 3))
+    # the batch-summed form (what gendr_backward_render_batchsum accumulates inside the backward kernel) goes to the same all-reduce
+    shared_presummed = parallel.allreduce_shared_face_grads(torch.from_numpy(gf).view(hi - lo, -1, 3, 3).sum(0).contiguous())
+    assert torch.allclose(shared, shared_presummed, rtol=1e-6, atol=1e-6 * float(shared.abs().max()))
     images = parallel.gather_images(torch.from_numpy(f['soft_colors']), B)
     # indexed / scene form of the same exchange: the gradient w.r.t. the batch-shared WORLD vertices [V,3] (camera backward of
     # the rank's views, numpy scene oracle) is a local sum + one all-reduce
