@@ -154,11 +154,15 @@ static size_t smem_bytes(const RenderParams& P, bool face_stationary_backward) {
 // 103 vs 112 ms at B = 16 -- pixel-stationary (pixel state in registers, one reduction per face per warp) when faces touch only
 // a few blocks -- C3: 5.97 vs 6.38 ms at B = 64.  The switch is the distribution's cull distance in pixels (>= 2 tiles => dense).
 // GENDR_B200_BWD=ps|fs forces one of them (A/B measurements).
-static int backward_mode(const RenderParams& P) {
+static int forced_backward_mode() {
     static const int forced = [] {
         const char* e = getenv("GENDR_B200_BWD");
         return (e && strcmp(e, "ps") == 0) ? 1 : ((e && strcmp(e, "fs") == 0) ? 0 : -1);
     }();
+    return forced;
+}
+static int backward_mode(const RenderParams& P) {
+    const int forced = forced_backward_mode();
     if (forced >= 0) return forced;
     const float reach_px = fminf(P.cull_radius, P.sqrt_thr) * 0.5f * (float)P.S;      // NaN / INF compare false => dense
     return (reach_px < 2.f * TILE_W) ? 1 : 0;
@@ -199,6 +203,15 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     LaunchCfg cfg;
     cfg.grid = dim3((unsigned)(P.B * P.tiles_x * P.tiles_y));
     cfg.bwd_mode = backward ? backward_mode(P) : 0;
+    if (backward && forced_backward_mode() < 0) {
+        // small problems: fewer CTAs than ~two waves of the machine (148 SMs x 4 CTAs).  The face-stationary kernel then also
+        // splits the faces across gridDim.y CTAs per tile (render_bwd_fs_kernel), whatever the density regime.
+        const long long ctas = (long long)P.B * P.tiles_x * P.tiles_y;
+        int splits = (int)((2 * 148 * 4 + ctas - 1) / (ctas > 0 ? ctas : 1));
+        splits = splits > 8 ? 8 : splits;
+        while (splits > 1 && P.F / splits < 64) --splits;
+        if (splits > 1) { cfg.bwd_mode = 0; cfg.grid.y = (unsigned)splits; }
+    }
     cfg.smem = smem_bytes(P, backward && cfg.bwd_mode == 0);
     cfg.stream = st;
     cfg.backward = backward;

@@ -5,6 +5,11 @@ Same call surface (names, defaults, name-or-id arguments, asserts), but the lean
 torch.empty and are fully written by one forward launch (the reference does 2 clones, 3 fills and 3 in-place scales
 first, renderer.py:130-151), the per-face records computed in forward are kept for backward, and texture gradients
 are only produced when `textures.requires_grad`.
+
+Host overhead (SURVEY 7 "hard part 5": tiny configurations are launch/host bound).  A call costs: one dictionary lookup for the
+cached C parameter struct, three torch.empty, one ctypes call, one autograd node with THREE inputs (the 19 scalars travel as one
+cached configuration object, so autograd neither wraps nor returns 19 Nones) -- no clones, no dtype/contiguity conversions unless
+the caller's tensors need them, no device-guard when the tensors already live on the current device.
 """
 import torch
 from torch.autograd import Function
@@ -33,61 +38,172 @@ def _resolve(value, table):
     return value if isinstance(value, int) else table[value]
 
 
+class _Config(object):
+    """One render configuration: the C parameter struct + the flags the host side needs.  Cached per distinct argument tuple."""
+    __slots__ = ('params', 'image_size', 'anti_aliasing')
+
+
+_CONFIG_CACHE = {}
+
+
+def _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
+            aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing):
+    try:
+        key = (image_size, background_color[0], background_color[1], background_color[2], dist_func, dist_scale, dist_squared, dist_shape,
+               dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far,
+               double_side, texture_type, anti_aliasing)
+        cfg = _CONFIG_CACHE.get(key)
+    except TypeError:                      # unhashable argument (e.g. a tensor-valued scale): build without caching
+        key, cfg = None, None
+    if cfg is None:
+        assert dist_scale >= 0, dist_scale      # functional/renderer.py:96
+        assert dist_eps >= 1, dist_eps          # functional/renderer.py:101
+        cfg = _Config()
+        cfg.params = _ext.make_params(
+            image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
+            _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
+            _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
+            TEXTURE_TYPE_IDS[texture_type], background_color)
+        cfg.image_size, cfg.anti_aliasing = int(image_size), bool(anti_aliasing)
+        if key is not None:
+            if len(_CONFIG_CACHE) > 512:
+                _CONFIG_CACHE.clear()
+            _CONFIG_CACHE[key] = cfg
+    return cfg
+
+
+def _f32c(t, device=None):
+    """float32, contiguous, on `device` -- without touching tensors that already are."""
+    if t.dtype is not torch.float32 or (device is not None and t.device != device):
+        t = t.to(device=device if device is not None else t.device, dtype=torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_WS_BYTES = {}
+
+
+def _workspace_bytes(B, F):
+    n = _WS_BYTES.get((B, F))
+    if n is None:
+        n = _WS_BYTES[(B, F)] = int(_ext._lib.load().gendr_workspace_bytes(B, F))
+    return n
+
+
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
+def _stream_of(device):
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _DeviceOf(object):
+    """`with torch.cuda.device(d)` only when d is not already the current device (the guard costs ~10 us)."""
+    __slots__ = ('guard',)
+
+    def __init__(self, device):
+        self.guard = None
+        if device.index is not None and device.index != torch.cuda.current_device():
+            self.guard = torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+
+
+def _forward_faces(ctx, face_vertices, textures, cfg):
+    if not face_vertices.is_cuda:
+        raise TypeError('GenDR only supports CUDA Tensors.')
+    faces = _f32c(face_vertices)
+    dev = faces.device
+    B, F = faces.shape[0], faces.shape[1]
+    tex = _f32c(textures, dev)
+    if tex.numel() == 0:
+        tex = tex.new_zeros((B, F, 1, 3))
+    elif tex.ndimension() != 4:
+        tex = tex.view(B, F, -1, 3)
+    S = cfg.image_size
+    soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=dev)
+    aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=dev)
+    workspace = torch.empty(_workspace_bytes(B, F), dtype=torch.uint8, device=dev)
+    lib = _ext._lib.load()
+    with _DeviceOf(dev):
+        if cfg.anti_aliasing:      # fused F.avg_pool2d(images, 2, 2) (gendr/renderer.py:92-93)
+            pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=dev)
+            _ext._lib.check(lib.gendr_forward_render_aa(faces.data_ptr(), tex.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
+                                                        pooled.data_ptr(), B, F, tex.shape[2], cfg.params, workspace.data_ptr(), workspace.numel(),
+                                                        _stream_of(dev)))
+        else:
+            pooled = None
+            _ext._lib.check(lib.gendr_forward_render(faces.data_ptr(), tex.data_ptr(), None, aggrs_info.data_ptr(), soft_colors.data_ptr(), B, F,
+                                                     tex.shape[2], cfg.params, 0, workspace.data_ptr(), workspace.numel(), _stream_of(dev)))
+    ctx.cfg = cfg
+    ctx.shapes = (face_vertices.shape, textures.shape)
+    ctx.save_for_backward(faces, tex, soft_colors, aggrs_info, workspace)
+    return pooled if cfg.anti_aliasing else soft_colors
+
+
+def _backward_faces(ctx, grad_soft_colors, want_tex):
+    faces, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
+    cfg = ctx.cfg
+    dev = faces.device
+    grad_soft_colors = _f32c(grad_soft_colors)
+    fshape, tshape = ctx.shapes
+    B, F = faces.shape[0], faces.shape[1]
+    grad_faces = torch.empty(fshape, dtype=torch.float32, device=dev)
+    grad_tex = torch.empty_like(tex) if want_tex else None
+    lib = _ext._lib.load()
+    fn = lib.gendr_backward_render_aa if cfg.anti_aliasing else lib.gendr_backward_render
+    with _DeviceOf(dev):
+        _ext._lib.check(fn(faces.data_ptr(), tex.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_faces.data_ptr(),
+                           grad_tex.data_ptr() if want_tex else None, grad_soft_colors.data_ptr(), B, F, tex.shape[2], cfg.params, 1, 1,
+                           workspace.data_ptr(), workspace.numel(), _stream_of(dev)))
+    if want_tex and grad_tex.shape != tshape:
+        grad_tex = grad_tex.view(tshape) if grad_tex.numel() == _numel(tshape) else grad_tex.new_zeros(tshape)      # (empty textures)
+    return grad_faces, grad_tex
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+class _RenderFaces(Function):
+    """render() proper: three autograd inputs (face_vertices, textures, configuration object)."""
+    @staticmethod
+    def forward(ctx, face_vertices, textures, cfg):
+        return _forward_faces(ctx, face_vertices, textures, cfg)
+
+    @staticmethod
+    def backward(ctx, grad_soft_colors):
+        grad_faces, grad_tex = _backward_faces(ctx, grad_soft_colors, ctx.needs_input_grad[1])
+        return grad_faces, grad_tex, None
+
+
 class GenDRFunction(Function):
+    """The reference's autograd.Function with its positional signature (functional/renderer.py:13-41); render() goes through the
+    three-input node above, this class is kept for code that calls GenDRFunction.apply directly."""
     @staticmethod
     def forward(ctx, face_vertices, textures, image_size=256, background_color=[0, 0, 0],
                 dist_func='uniform', dist_scale=1e-2, dist_squared=False, dist_shape=None, dist_shift=None,
                 dist_eps=1e4, aggr_alpha_func='probabilistic', aggr_alpha_t_conorm_p=None,
                 aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3, near=1, far=100,
                 double_side=True, texture_type='surface', anti_aliasing=False):
-        assert dist_scale >= 0, dist_scale      # functional/renderer.py:96
-        assert dist_eps >= 1, dist_eps          # functional/renderer.py:101
-        if not face_vertices.is_cuda:
-            raise TypeError('GenDR only supports CUDA Tensors.')
-        params = _ext.make_params(
-            image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
-            _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
-            _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
-            TEXTURE_TYPE_IDS[texture_type], background_color)
-
-        faces = face_vertices.detach().to(torch.float32).contiguous()
-        B, F = faces.shape[:2]
-        faces = faces.view(B, F, 9)
-        tex = textures.detach().to(device=faces.device, dtype=torch.float32).contiguous()
-        tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
-        S = int(image_size)
-        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=faces.device)
-        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=faces.device)
-        workspace = _ext.workspace_for(faces)
-        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=faces.device) if anti_aliasing else None
-        with torch.cuda.device(faces.device):
-            if anti_aliasing:      # fused F.avg_pool2d(images, 2, 2) (gendr/renderer.py:92-93)
-                _ext.forward_render_aa_raw(faces, tex, aggrs_info, soft_colors, pooled, params, workspace)
-            else:
-                _ext.forward_render_raw(faces, tex, None, aggrs_info, soft_colors, params, False, workspace)
-        ctx.params, ctx.anti_aliasing = params, bool(anti_aliasing)
-        ctx.shapes = (face_vertices.shape, textures.shape)
-        ctx.save_for_backward(faces, tex, soft_colors, aggrs_info, workspace)
-        if anti_aliasing:
-            return pooled
-        return soft_colors
+        cfg = _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
+                      aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing)
+        return _forward_faces(ctx, face_vertices, textures, cfg)
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
-        faces, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
-        grad_soft_colors = grad_soft_colors.to(torch.float32).contiguous()
-        want_tex = ctx.needs_input_grad[1]
-        grad_faces = torch.empty_like(faces)
-        grad_tex = torch.empty_like(tex) if want_tex else None
-        with torch.cuda.device(faces.device):
-            if ctx.anti_aliasing:
-                _ext.backward_render_aa_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
-                                            ctx.params, workspace, True, True)
-            else:
-                _ext.backward_render_raw(faces, tex, soft_colors, aggrs_info, grad_faces, grad_tex, grad_soft_colors,
-                                         ctx.params, workspace, True, True)
-        fshape, tshape = ctx.shapes
-        return (grad_faces.view(fshape), grad_tex.view(tshape) if want_tex else None) + (None,) * 18
+        grad_faces, grad_tex = _backward_faces(ctx, grad_soft_colors, ctx.needs_input_grad[1])
+        return (grad_faces, grad_tex) + (None,) * 18
 
 
 # Face indices are checked ONCE per index tensor object (one min/max reduction + host sync; a mesh keeps its faces tensor across
@@ -108,65 +224,72 @@ def check_face_indices(faces, num_vertices):
         pass
 
 
+def _index_i32(faces, device):
+    """int32, contiguous, on `device`; the converted tensor is cached on the caller's index tensor (meshes keep their faces)."""
+    if faces.dtype is torch.int32 and faces.device == device and faces.is_contiguous():
+        return faces
+    mark = (faces._version, str(device))
+    cached = getattr(faces, '_gendr_i32', None)
+    if cached is not None and cached[0] == mark:
+        return cached[1]
+    index = faces.detach().to(device=device, dtype=torch.int32).contiguous()
+    try:
+        faces._gendr_i32 = (mark, index)
+    except AttributeError:
+        pass
+    return index
+
+
 class GenDRIndexedFunction(Function):
     """render() for an indexed mesh: (vertices [B,V,3] screen space, faces [B,F,3] or [F,3] int) instead of the gathered
     face_vertices [B,F,3,3].  The gather runs inside the face preprocessing kernel and the gradient is scatter-added
     into grad_vertices [B,V,3] by the backward kernel (replaces gendr/functional/face_vertices.py:27 and its
     index_put backward)."""
     @staticmethod
-    def forward(ctx, vertices, faces, textures, image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape,
-                dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma,
-                near, far, double_side, texture_type, anti_aliasing=False):
-        assert dist_scale >= 0, dist_scale
-        assert dist_eps >= 1, dist_eps
+    def forward(ctx, vertices, faces, textures, cfg):
         if not vertices.is_cuda:
             raise TypeError('GenDR only supports CUDA Tensors.')
-        params = _ext.make_params(
-            image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
-            _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
-            _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
-            TEXTURE_TYPE_IDS[texture_type], background_color)
-        verts = vertices.detach().to(torch.float32).contiguous()
-        B, V = verts.shape[:2]
+        verts = _f32c(vertices)
+        dev = verts.device
+        B, V = verts.shape[0], verts.shape[1]
         check_face_indices(faces, V)
-        index = faces.detach().to(device=verts.device, dtype=torch.int32).contiguous()
+        index = _index_i32(faces, dev)
         shared = index.ndimension() == 2
         F = index.shape[-2]
-        tex = textures.detach().to(device=verts.device, dtype=torch.float32).contiguous()
+        tex = _f32c(textures, dev)
         tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
-        S = int(image_size)
-        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=verts.device)
-        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=verts.device)
+        S = cfg.image_size
+        soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=dev)
+        aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=dev)
         lib = _ext._lib.load()
-        workspace = torch.empty(lib.gendr_workspace_bytes(B, F), dtype=torch.uint8, device=verts.device)
-        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=verts.device) if anti_aliasing else None
-        with torch.cuda.device(verts.device):
+        workspace = torch.empty(_workspace_bytes(B, F), dtype=torch.uint8, device=dev)
+        pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=dev) if cfg.anti_aliasing else None
+        with _DeviceOf(dev):
             _ext._lib.check(lib.gendr_forward_render_indexed(
                 verts.data_ptr(), index.data_ptr(), int(shared), tex.data_ptr(), aggrs_info.data_ptr(), soft_colors.data_ptr(),
-                pooled.data_ptr() if anti_aliasing else None, B, V, F, int(tex.shape[2]), params, workspace.data_ptr(),
-                workspace.numel(), torch.cuda.current_stream(verts.device).cuda_stream))
-        ctx.params, ctx.dims, ctx.shapes = params, (B, V, F, int(tex.shape[2]), shared), (vertices.shape, textures.shape)
-        ctx.anti_aliasing = bool(anti_aliasing)
+                pooled.data_ptr() if cfg.anti_aliasing else None, B, V, F, int(tex.shape[2]), cfg.params, workspace.data_ptr(),
+                workspace.numel(), _stream_of(dev)))
+        ctx.cfg, ctx.dims, ctx.shapes = cfg, (B, V, F, int(tex.shape[2]), shared), (vertices.shape, textures.shape)
         ctx.save_for_backward(index, tex, soft_colors, aggrs_info, workspace)
-        return pooled if anti_aliasing else soft_colors
+        return pooled if cfg.anti_aliasing else soft_colors
 
     @staticmethod
     def backward(ctx, grad_soft_colors):
         index, tex, soft_colors, aggrs_info, workspace = ctx.saved_tensors
         B, V, F, T, shared = ctx.dims
-        grad_soft_colors = grad_soft_colors.to(torch.float32).contiguous()
+        cfg = ctx.cfg
+        grad_soft_colors = _f32c(grad_soft_colors)
         want_tex = ctx.needs_input_grad[2]
         grad_vertices = torch.empty((B, V, 3), dtype=torch.float32, device=tex.device)
         grad_tex = torch.empty_like(tex) if want_tex else None
         lib = _ext._lib.load()
-        with torch.cuda.device(tex.device):
+        with _DeviceOf(tex.device):
             _ext._lib.check(lib.gendr_backward_render_indexed(
                 index.data_ptr(), int(shared), tex.data_ptr(), soft_colors.data_ptr(), aggrs_info.data_ptr(),
                 grad_vertices.data_ptr(), grad_tex.data_ptr() if want_tex else None, grad_soft_colors.data_ptr(),
-                int(ctx.anti_aliasing), B, V, F, T, ctx.params, 1, workspace.data_ptr(), workspace.numel(),
-                torch.cuda.current_stream(tex.device).cuda_stream))
+                int(cfg.anti_aliasing), B, V, F, T, cfg.params, 1, workspace.data_ptr(), workspace.numel(), _stream_of(tex.device)))
         vshape, tshape = ctx.shapes
-        return (grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None) + (None,) * 18
+        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, None
 
 
 def render_indexed(vertices, faces, textures, image_size=256, background_color=[0, 0, 0],
@@ -175,10 +298,9 @@ def render_indexed(vertices, faces, textures, image_size=256, background_color=[
                    aggr_rgb_func='softmax', aggr_rgb_eps=1e-3, aggr_rgb_gamma=1e-3,
                    near=1, far=100, double_side=True, texture_type='surface', anti_aliasing=False):
     """Same as render(), for (vertices [B,V,3], faces [B,F,3] | [F,3]) instead of face_vertices [B,F,3,3]."""
-    return GenDRIndexedFunction.apply(vertices, faces, textures, image_size, background_color, dist_func, dist_scale,
-                                      dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
-                                      aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type,
-                                      anti_aliasing)
+    cfg = _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
+                  aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing)
+    return GenDRIndexedFunction.apply(vertices, faces, textures, cfg)
 
 
 def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
@@ -190,14 +312,20 @@ def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
     Keyword surface and defaults of gendr.functional.render (functional/renderer.py:239-262).  One addition:
     anti_aliasing=True treats image_size as the supersampled side and returns the 2x2-averaged image
     [B,4,S/2,S/2] -- F.avg_pool2d(render(...), 2, 2) of gendr/renderer.py:92-93, fused into the kernels (bit-identical)."""
-    return GenDRFunction.apply(face_vertices, textures, image_size, background_color, dist_func, dist_scale,
-                               dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func, aggr_alpha_t_conorm_p,
-                               aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type,
-                               anti_aliasing)
+    cfg = _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
+                  aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing)
+    return _RenderFaces.apply(face_vertices, textures, cfg)
+
+
+_CAMERA_CACHE, _LIGHT_CACHE = {}, {}
 
 
 def make_camera_params(mode='look_at', perspective=True, viewing_angle=30., viewing_scale=1.0, at=(0, 0, 0), up=(0, 1, 0),
                        direction=(0, 0, 1)):
+    key = (mode, perspective, viewing_angle, viewing_scale, tuple(at), tuple(up), tuple(direction))
+    c = _CAMERA_CACHE.get(key)
+    if c is not None:
+        return c
     c = _ext._lib.CameraParams()
     c.mode = {'look_at': 0, 'look': 1}[mode]
     c.perspective = int(bool(perspective))
@@ -206,18 +334,31 @@ def make_camera_params(mode='look_at', perspective=True, viewing_angle=30., view
     for k in range(3):
         c.at_or_direction[k] = float(target[k])
         c.up[k] = float(up[k])
+    if len(_CAMERA_CACHE) > 256:
+        _CAMERA_CACHE.clear()
+    _CAMERA_CACHE[key] = c
     return c
 
 
 def make_light_params(intensity_ambient=0.5, color_ambient=(1, 1, 1), intensity_directional=0.5,
                       color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    key = (intensity_ambient, tuple(color_ambient), intensity_directional, tuple(color_directional), tuple(direction))
+    p = _LIGHT_CACHE.get(key)
+    if p is not None:
+        return p
     p = _ext._lib.LightParams()
     p.intensity_ambient, p.intensity_directional = float(intensity_ambient), float(intensity_directional)
     for k in range(3):
         p.color_ambient[k] = float(color_ambient[k])
         p.color_directional[k] = float(color_directional[k])
         p.direction[k] = float(direction[k])
+    if len(_LIGHT_CACHE) > 256:
+        _LIGHT_CACHE.clear()
+    _LIGHT_CACHE[key] = p
     return p
+
+
+_SCENE_WS_BYTES = {}
 
 
 class GenDRSceneFunction(Function):
@@ -227,12 +368,12 @@ class GenDRSceneFunction(Function):
     backward (gendr_scene_forward / gendr_scene_backward); gradients w.r.t. the world-space vertices (camera path +
     normals' path) and the unlit textures."""
     @staticmethod
-    def forward(ctx, vertices, faces, textures, eyes, camera, light, params, anti_aliasing):
+    def forward(ctx, vertices, faces, textures, eyes, camera, light, cfg):
         if not vertices.is_cuda:
             raise TypeError('GenDR only supports CUDA Tensors.')
-        verts = vertices.detach().to(torch.float32).contiguous()
+        verts = _f32c(vertices)
         dev = verts.device
-        eyes = eyes.detach().to(device=dev, dtype=torch.float32).contiguous()
+        eyes = _f32c(eyes, dev)
         eyes_batched = eyes.ndimension() == 2
         # vertices [V,3]: ONE mesh seen from every eye (the shared-mesh pattern of experiments/opt_shape.py:86 without
         # vertices.repeat(batch, 1, 1)); the gradient comes back batch-summed as [V,3]
@@ -241,47 +382,51 @@ class GenDRSceneFunction(Function):
             V = verts.shape[0]
             B = eyes.shape[0] if eyes_batched else int(textures.shape[0])
         else:
-            B, V = verts.shape[:2]
+            B, V = verts.shape[0], verts.shape[1]
         check_face_indices(faces, V)
-        index = faces.detach().to(device=dev, dtype=torch.int32).contiguous()
+        index = _index_i32(faces, dev)
         shared = index.ndimension() == 2
         F = index.shape[-2]
-        tex = textures.detach().to(device=dev, dtype=torch.float32).contiguous()
+        tex = _f32c(textures, dev)
         tex = tex.view(B, F, -1, 3) if tex.numel() else tex.new_zeros((B, F, 1, 3))
         T = int(tex.shape[2])
         if eyes_batched and eyes.shape[0] != B:
             raise ValueError('eyes must be [3] or [batch, 3]')
-        S = int(params.image_size)
+        S = cfg.image_size
+        anti_aliasing = cfg.anti_aliasing
         soft_colors = torch.empty((B, 4, S, S), dtype=torch.float32, device=dev)
         aggrs_info = torch.empty((B, 2, S, S), dtype=torch.float32, device=dev)
         pooled = torch.empty((B, 4, S // 2, S // 2), dtype=torch.float32, device=dev) if anti_aliasing else None
         lib = _ext._lib.load()
-        workspace = torch.empty(lib.gendr_scene_workspace_bytes(B, V, F, T), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        nws = _SCENE_WS_BYTES.get((B, V, F, T))
+        if nws is None:
+            nws = _SCENE_WS_BYTES[(B, V, F, T)] = int(lib.gendr_scene_workspace_bytes(B, V, F, T))
+        workspace = torch.empty(nws, dtype=torch.uint8, device=dev)
+        with _DeviceOf(dev):
             _ext._lib.check(lib.gendr_scene_forward(
                 verts.data_ptr(), int(verts_shared), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
-                aggrs_info.data_ptr(), soft_colors.data_ptr(), pooled.data_ptr() if anti_aliasing else None, B, V, F, T, params,
-                workspace.data_ptr(), workspace.numel(), torch.cuda.current_stream(dev).cuda_stream))
-        ctx.cfg = (camera, light, params, bool(anti_aliasing), (B, V, F, T, shared, eyes_batched, verts_shared), (vertices.shape, textures.shape))
+                aggrs_info.data_ptr(), soft_colors.data_ptr(), pooled.data_ptr() if anti_aliasing else None, B, V, F, T, cfg.params,
+                workspace.data_ptr(), workspace.numel(), _stream_of(dev)))
+        ctx.cfg = (camera, light, cfg, (B, V, F, T, shared, eyes_batched, verts_shared), (vertices.shape, textures.shape))
         ctx.save_for_backward(verts, index, tex, eyes, soft_colors, aggrs_info, workspace)
         return pooled if anti_aliasing else soft_colors
 
     @staticmethod
     def backward(ctx, grad_images):
         verts, index, tex, eyes, soft_colors, aggrs_info, workspace = ctx.saved_tensors
-        camera, light, params, aa, (B, V, F, T, shared, eyes_batched, verts_shared), (vshape, tshape) = ctx.cfg
-        grad_images = grad_images.to(torch.float32).contiguous()
+        camera, light, cfg, (B, V, F, T, shared, eyes_batched, verts_shared), (vshape, tshape) = ctx.cfg
+        grad_images = _f32c(grad_images)
         want_tex = ctx.needs_input_grad[2]
         grad_vertices = torch.empty_like(verts)
         grad_tex = torch.empty_like(tex) if want_tex else None
         lib = _ext._lib.load()
-        with torch.cuda.device(verts.device):
+        with _DeviceOf(verts.device):
             _ext._lib.check(lib.gendr_scene_backward(
                 verts.data_ptr(), int(verts_shared), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
-                soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_images.data_ptr(), int(aa), grad_vertices.data_ptr(),
-                grad_tex.data_ptr() if want_tex else None, B, V, F, T, params, workspace.data_ptr(), workspace.numel(),
-                torch.cuda.current_stream(verts.device).cuda_stream))
-        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, None, None, None, None, None
+                soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_images.data_ptr(), int(cfg.anti_aliasing), grad_vertices.data_ptr(),
+                grad_tex.data_ptr() if want_tex else None, B, V, F, T, cfg.params, workspace.data_ptr(), workspace.numel(),
+                _stream_of(verts.device)))
+        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, None, None, None, None
 
 
 def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, image_size=256, background_color=[0, 0, 0],
@@ -296,15 +441,10 @@ def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, im
     to its single all-reduce (gendr_b200.parallel.allreduce_shared_vertex_grads).
     camera: dict for make_camera_params (mode, perspective, viewing_angle, viewing_scale, at, up, direction);
     lighting: dict for make_light_params, or None for no lighting step."""
-    assert dist_scale >= 0, dist_scale
-    assert dist_eps >= 1, dist_eps
     if texture_type != 'surface':
         raise ValueError('render_scene supports surface textures only')
-    params = _ext.make_params(
-        image_size, _resolve(dist_func, DIST_FUNC_IDS), dist_scale, dist_squared, dist_shape, dist_shift, dist_eps,
-        _resolve(aggr_alpha_func, AGGR_ALPHA_FUNC_IDS), aggr_alpha_t_conorm_p,
-        _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
-        TEXTURE_TYPE_IDS[texture_type], background_color)
+    cfg = _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
+                  aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing)
     cam = make_camera_params(**(camera or {}))
     light = make_light_params(**lighting) if lighting is not None else None
     if not torch.is_tensor(eyes):
@@ -312,4 +452,4 @@ def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, im
     if eyes.requires_grad:
         raise ValueError('render_scene does not differentiate w.r.t. the camera position: use LookAt/Look (torch path) for eyes that '
                          'require a gradient (experiments/opt_camera.py)')
-    return GenDRSceneFunction.apply(vertices, faces, textures, eyes, cam, light, params, anti_aliasing)
+    return GenDRSceneFunction.apply(vertices, faces, textures, eyes, cam, light, cfg)

@@ -31,6 +31,23 @@ class DirectionalLighting(nn.Module):
         return functional.directional_lighting(light, normals, self.light_intensity, self.light_color, self.light_direction)
 
 
+class _LightSnapshot(object):
+    """What a deferred Lighting step needs later: the fused-kernel parameters (a plain dict, snapshot at call time) and the torch
+    implementation for meshes that get materialised instead.  (A deepcopy of the nn.Module costs ~100 us per call.)"""
+    __slots__ = ('params',)
+
+    def __init__(self, params):
+        self.params = params
+
+    def fused_params(self):
+        return self.params
+
+    def lit_textures(self, mesh):
+        p = self.params
+        return Lighting(p['intensity_ambient'], list(p['color_ambient']), p['intensity_directional'], list(p['color_directional']),
+                        list(p['direction'])).lit_textures(mesh)
+
+
 class Lighting(nn.Module):
     def __init__(self, intensity_ambient=0.5, color_ambient=[1, 1, 1], intensity_directionals=0.5,
                  color_directionals=[1, 1, 1], directions=[0, 1, 0]):
@@ -67,8 +84,10 @@ class Lighting(nn.Module):
 
     def forward(self, mesh):
         if (_mesh.FUSE_SCENE and mesh.texture_type == 'surface' and mesh._pending_light is None and mesh._pending_camera is None
-                and mesh._vertices.is_cuda and self.fused_params() is not None):
-            # deferred: GenDR.forward runs the lighting kernel (or .textures materialises it with lit_textures)
-            return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,
-                        _pending_light=copy.deepcopy(self))
+                and mesh._vertices.is_cuda):
+            params = self.fused_params()
+            if params is not None:
+                # deferred: GenDR.forward runs the lighting kernel (or .textures materialises it with lit_textures)
+                return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,
+                            _pending_light=_LightSnapshot(params))
         return Mesh(mesh.vertices, mesh.faces, self.lit_textures(mesh), mesh.texture_res, mesh.texture_type)
