@@ -51,12 +51,12 @@ SIGNATURES = {
     'gendr_forward_render_aa': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _PP, _P, _SZ, _P]),
     'gendr_backward_render_aa': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _PP, _I, _I, _P, _SZ, _P]),
     'gendr_camera_forward': (_I, [_P, _P, _I, _P, _I, _I, _PC, _P]),
-    'gendr_camera_backward': (_I, [_P, _P, _I, _P, _P, _I, _I, _PC, _P]),
+    'gendr_camera_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _PC, _P]),
     'gendr_lighting_forward': (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _PL, _P]),
     'gendr_lighting_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _PL, _P]),
     'gendr_scene_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
     'gendr_scene_forward': (_I, [_P, _I, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
-    'gendr_scene_backward': (_I, [_P, _I, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
+    'gendr_scene_backward': (_I, [_P, _I, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
     'gendr_voxelize_workspace_bytes': (_SZ, [_I, _I]),
     'gendr_voxelize': (_I, [_P, _P, _I, _I, _I, _P, _SZ, _P]),
     'gendr_render_forward_backward_host': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _PP]),

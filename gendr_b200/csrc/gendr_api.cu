@@ -715,13 +715,23 @@ static int camera_forward_impl(const CameraParams& C, const float* vertices, lon
     GENDR_CUDA(cudaGetLastError(), "camera_forward_kernel launch");
     return 0;
 }
+// grad_eyes (may be null): [B,3], or [3] when one eye is shared by the batch; eye_acc: [B,12] scratch (required with grad_eyes)
 static int camera_backward_impl(const CameraParams& C, const float* vertices, long long vstride, const float* eyes, const float* grad_screen,
-                                float* grad_vertices, int B, int V, cudaStream_t st) {
+                                float* grad_vertices, float* grad_eyes, float* eye_acc, int B, int V, cudaStream_t st) {
     const long long n = (long long)B * V;
     if (n == 0) return 0;
-    camera_backward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, vstride, eyes, grad_screen, grad_vertices, B, V);
+    if (grad_eyes) {
+        GENDR_CUDA(cudaMemsetAsync(eye_acc, 0, (size_t)B * 12 * sizeof(float), st), "zero eye-gradient accumulators");
+        if (C.eye_stride == 0) GENDR_CUDA(cudaMemsetAsync(grad_eyes, 0, 3 * sizeof(float), st), "zero grad_eyes");
+    }
+    camera_backward_kernel<<<blocks_for(n), 256, 0, st>>>(C, vertices, vstride, eyes, grad_screen, grad_vertices, grad_eyes ? eye_acc : nullptr, B, V);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "camera_backward_kernel launch");
+    if (grad_eyes) {
+        camera_eye_grad_kernel<<<(B + 127) / 128, 128, 0, st>>>(C, eyes, eye_acc, grad_eyes, B);
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "camera_eye_grad_kernel launch");
+    }
     return 0;
 }
 static int lighting_forward_impl(const LightParams& L, const float* vertices, long long vstride, const int* face_index, int index_shared,
@@ -757,15 +767,16 @@ int gendr_camera_forward(const float* vertices, const float* eyes, int eyes_batc
 }
 
 int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_batched, const float* grad_screen_vertices, float* grad_vertices,
-                          int batch, int num_vertices, const gendr_camera_params* camera, void* stream) {
+                          float* grad_eyes, float* eye_scratch, int batch, int num_vertices, const gendr_camera_params* camera, void* stream) {
     CameraParams C;
     if (make_camera(C, camera, eyes_batched) || batch < 0 || num_vertices < 0) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_camera_backward");
     if (batch == 0 || num_vertices == 0) return 0;
-    if (!vertices || !eyes || !grad_screen_vertices || !grad_vertices) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_backward");
+    if (!vertices || !eyes || !grad_screen_vertices || !grad_vertices || (grad_eyes && !eye_scratch))
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_camera_backward");
     DeviceScope dev;
     GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
-    return camera_backward_impl(C, vertices, (long long)num_vertices * 3, eyes, grad_screen_vertices, grad_vertices, batch, num_vertices,
-                                reinterpret_cast<cudaStream_t>(stream));
+    return camera_backward_impl(C, vertices, (long long)num_vertices * 3, eyes, grad_screen_vertices, grad_vertices, grad_eyes, eye_scratch, batch,
+                                num_vertices, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int gendr_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, float* lit_textures, int batch,
@@ -795,8 +806,9 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
                                   num_vertices, num_faces, texture_size, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// scene workspace: [render workspace | screen vertices B*V*3 | grad screen vertices B*V*3 | lit textures B*F*T*3 | grad lit B*F*T*3]
-struct SceneWs { void* render; float* screen; float* grad_screen; float* lit; float* grad_lit; };
+// scene workspace: [render workspace | screen vertices B*V*3 | grad screen vertices B*V*3 | lit textures B*F*T*3 | grad lit B*F*T*3 |
+//                   eye-gradient accumulators B*12]
+struct SceneWs { void* render; float* screen; float* grad_screen; float* lit; float* grad_lit; float* eye_acc; };
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 static SceneWs scene_ws(void* ws, int B, int V, int F, int T) {
     SceneWs w;
@@ -805,13 +817,14 @@ static SceneWs scene_ws(void* ws, int B, int V, int F, int T) {
     w.screen = reinterpret_cast<float*>(p); p += al256((size_t)B * V * 12);
     w.grad_screen = reinterpret_cast<float*>(p); p += al256((size_t)B * V * 12);
     w.lit = reinterpret_cast<float*>(p); p += al256((size_t)B * F * T * 12);
-    w.grad_lit = reinterpret_cast<float*>(p);
+    w.grad_lit = reinterpret_cast<float*>(p); p += al256((size_t)B * F * T * 12);
+    w.eye_acc = reinterpret_cast<float*>(p);
     return w;
 }
 size_t gendr_scene_workspace_bytes(int batch, int num_vertices, int num_faces, int texture_size) {
     if (batch < 0 || num_vertices < 0 || num_faces < 0 || texture_size < 1) return 0;
     return al256(gendr_workspace_bytes(batch, num_faces)) + 2 * al256((size_t)batch * num_vertices * 12) +
-           2 * al256((size_t)batch * num_faces * texture_size * 12) + 256;
+           2 * al256((size_t)batch * num_faces * texture_size * 12) + al256((size_t)batch * 48) + 256;
 }
 
 int gendr_scene_forward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
@@ -847,8 +860,8 @@ int gendr_scene_forward(const float* vertices, int vertices_shared, const int* f
 
 int gendr_scene_backward(const float* vertices, int vertices_shared, const int* face_index, int index_shared, const float* textures, const float* eyes, int eyes_batched,
                          const gendr_camera_params* camera, const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
-                         const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures, int batch,
-                         int num_vertices, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
+                         const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures, float* grad_eyes,
+                         int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params, void* workspace,
                          size_t workspace_bytes, void* stream) {
     RenderParams P;
     CameraParams C;
@@ -874,7 +887,7 @@ int gendr_scene_backward(const float* vertices, int vertices_shared, const int* 
                                       grad_soft_colors, grad_is_pooled, num_vertices, 0, w.render, st)) return e;
     const long long vstride = vertices_shared ? 0 : (long long)num_vertices * 3;
     if (vertices_shared) GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)num_vertices * 12, st), "zero the batch-summed vertex gradient");
-    if (int e = camera_backward_impl(C, vertices, vstride, eyes, w.grad_screen, grad_vertices, batch, num_vertices, st)) return e;
+    if (int e = camera_backward_impl(C, vertices, vstride, eyes, w.grad_screen, grad_vertices, grad_eyes, w.eye_acc, batch, num_vertices, st)) return e;
     if (light) {
         LightParams L;
         make_light(L, light);

@@ -104,19 +104,23 @@ __global__ void __launch_bounds__(256) camera_forward_kernel(const __grid_consta
 
 // ---- backward: grad_screen [B,V,3] -> grad_vertices [B,V,3] (plain store: every thread owns its vertex), or, for a mesh shared
 // by the batch (vstride == 0), red.add into the batch-summed grad_vertices [V,3] (zero-filled by the caller) --------------------
+// eye_acc (may be null): [B][12] zero-filled accumulators for the gradient w.r.t. the camera position (experiments/opt_camera.py
+// optimises the eye): sum_v grad_v (3) | sum_v gxc*d (3) | sum_v gyc*d (3) | sum_v gzc*d (3) with d = v - eye; camera_eye_grad_kernel
+// turns them into d loss / d eye.
 __global__ void __launch_bounds__(256) camera_backward_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ vertices,
                                                               long long vstride, const float* __restrict__ eyes,
-                                                              const float* __restrict__ grad_screen, float* __restrict__ grad_vertices, int B,
-                                                              int V) {
+                                                              const float* __restrict__ grad_screen, float* __restrict__ grad_vertices,
+                                                              float* __restrict__ eye_acc, int B, int V) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)B * V) return;
-    const int b = (int)(i / V);
-    const long long v = i - (long long)b * V;
+    const bool in_range = i < (long long)B * V;
+    if (!in_range && !eye_acc) return;
+    const int b = in_range ? (int)(i / V) : B - 1;
+    const long long v = in_range ? i - (long long)b * V : 0;
     const CameraBasis K = camera_basis(C, eyes, b);
-    const f3 g = load3(grad_screen + i * 3);
+    const f3 g = in_range ? load3(grad_screen + i * 3) : mk3(0.f, 0.f, 0.f);
     float gxc, gyc, gzc;
+    const f3 d = sub3(load3(vertices + b * vstride + v * 3), K.eye);
     if (C.perspective) {
-        const f3 d = sub3(load3(vertices + b * vstride + v * 3), K.eye);
         const float xc = dot3_gemm(d, K.x), yc = dot3_gemm(d, K.y), zc = dot3_gemm(d, K.z);
         const float r = 1.f / (zc * tanf(C.angle_rad));              // d(xs)/d(xc)
         gxc = g.x * r; gyc = g.y * r;
@@ -127,10 +131,79 @@ __global__ void __launch_bounds__(256) camera_backward_kernel(const __grid_const
     // v_cam = R (v - eye)  =>  grad_v = R^T grad_cam
     const float gx = gxc * K.x.x + gyc * K.y.x + gzc * K.z.x, gy = gxc * K.x.y + gyc * K.y.y + gzc * K.z.y,
                 gz = gxc * K.x.z + gyc * K.y.z + gzc * K.z.z;
-    if (vstride != 0) {
-        grad_vertices[i * 3 + 0] = gx; grad_vertices[i * 3 + 1] = gy; grad_vertices[i * 3 + 2] = gz;
+    if (in_range) {
+        if (vstride != 0) {
+            grad_vertices[i * 3 + 0] = gx; grad_vertices[i * 3 + 1] = gy; grad_vertices[i * 3 + 2] = gz;
+        } else {
+            atomicAdd(grad_vertices + v * 3 + 0, gx); atomicAdd(grad_vertices + v * 3 + 1, gy); atomicAdd(grad_vertices + v * 3 + 2, gz);
+        }
+    }
+    if (eye_acc) {
+        float t[12] = {gx, gy, gz, gxc * d.x, gxc * d.y, gxc * d.z, gyc * d.x, gyc * d.y, gyc * d.z, gzc * d.x, gzc * d.y, gzc * d.z};
+        if (!in_range) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) t[k] = 0.f;
+        }
+        const unsigned full = 0xffffffffu;
+        const int b0 = __shfl_sync(full, b, 0);
+        if (__all_sync(full, b == b0)) {          // the usual case: the whole warp belongs to one batch item
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_xor_sync(full, t[k], o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) atomicAdd(eye_acc + (size_t)b * 12 + k, t[k]);
+            }
+        } else if (in_range) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) atomicAdd(eye_acc + (size_t)b * 12 + k, t[k]);
+        }
+    }
+}
+
+// F.normalize backward: u = v / max(|v|, eps); returns d loss / d v from d loss / d u
+__device__ __forceinline__ f3 normalize3_bwd(f3 v, float eps, f3 gu) {
+    const float n = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    if (!(n > eps)) return scale3(gu, 1.f / eps);
+    const f3 u = scale3(v, 1.f / n);
+    const float ug = u.x * gu.x + u.y * gu.y + u.z * gu.z;
+    return scale3(mk3(gu.x - u.x * ug, gu.y - u.y * ug, gu.z - u.z * ug), 1.f / n);
+}
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 cross3p(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+
+// d loss / d eye from the accumulators of camera_backward_kernel: the translation term -sum_v grad_v, plus (look_at mode) the
+// path through the rotation rows z = normalize(at - eye), x = normalize(up x z), y = normalize(z x x)   (look_at.py:52-66).
+// One thread per batch item; grad_eyes is [B,3], or [3] accumulated over the batch when one eye is shared (eye_stride == 0).
+__global__ void __launch_bounds__(128) camera_eye_grad_kernel(const __grid_constant__ CameraParams C, const float* __restrict__ eyes,
+                                                              const float* __restrict__ eye_acc, float* __restrict__ grad_eyes, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* a = eye_acc + (size_t)b * 12;
+    f3 ge = mk3(-a[0], -a[1], -a[2]);                                   // v - eye
+    if (C.mode == 0) {
+        const f3 eye = load3(eyes + (size_t)b * C.eye_stride);
+        const f3 at = mk3(C.at_or_dir[0], C.at_or_dir[1], C.at_or_dir[2]), up = mk3(C.up[0], C.up[1], C.up[2]);
+        const f3 q = sub3(at, eye);
+        const f3 z = normalize3(q, 1e-5f);
+        const f3 p = cross3(up, z);
+        const f3 x = normalize3(p, 1e-5f);
+        const f3 s2 = cross3(z, x);
+        f3 gx = mk3(a[3], a[4], a[5]), gy = mk3(a[6], a[7], a[8]), gz = mk3(a[9], a[10], a[11]);
+        const f3 gs = normalize3_bwd(s2, 1e-5f, gy);                    // y = normalize(z x x)
+        gz = add3(gz, cross3p(x, gs));                                  // c = a x b: ga = b x gc, gb = gc x a
+        gx = add3(gx, cross3p(gs, z));
+        const f3 gp = normalize3_bwd(p, 1e-5f, gx);                     // x = normalize(up x z)
+        gz = add3(gz, cross3p(gp, up));
+        const f3 gq = normalize3_bwd(q, 1e-5f, gz);                     // z = normalize(at - eye)
+        ge = sub3(ge, gq);
+    }
+    if (C.eye_stride != 0) {
+        grad_eyes[(size_t)b * 3 + 0] = ge.x; grad_eyes[(size_t)b * 3 + 1] = ge.y; grad_eyes[(size_t)b * 3 + 2] = ge.z;
     } else {
-        atomicAdd(grad_vertices + v * 3 + 0, gx); atomicAdd(grad_vertices + v * 3 + 1, gy); atomicAdd(grad_vertices + v * 3 + 2, gz);
+        atomicAdd(grad_eyes + 0, ge.x); atomicAdd(grad_eyes + 1, ge.y); atomicAdd(grad_eyes + 2, ge.z);
     }
 }
 

@@ -373,7 +373,9 @@ class GenDRSceneFunction(Function):
             raise TypeError('GenDR only supports CUDA Tensors.')
         verts = _f32c(vertices)
         dev = verts.device
-        eyes = _f32c(eyes, dev)
+        if eyes.dtype is not torch.float32 or eyes.device != dev or eyes.ndimension() not in (1, 2) or eyes.shape[-1] != 3:
+            raise ValueError('eyes must be a float32 tensor [3] or [batch, 3] on the device of the vertices')
+        eyes = eyes if eyes.is_contiguous() else eyes.contiguous()
         eyes_batched = eyes.ndimension() == 2
         # vertices [V,3]: ONE mesh seen from every eye (the shared-mesh pattern of experiments/opt_shape.py:86 without
         # vertices.repeat(batch, 1, 1)); the gradient comes back batch-summed as [V,3]
@@ -416,17 +418,18 @@ class GenDRSceneFunction(Function):
         verts, index, tex, eyes, soft_colors, aggrs_info, workspace = ctx.saved_tensors
         camera, light, cfg, (B, V, F, T, shared, eyes_batched, verts_shared), (vshape, tshape) = ctx.cfg
         grad_images = _f32c(grad_images)
-        want_tex = ctx.needs_input_grad[2]
+        want_tex, want_eye = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
         grad_vertices = torch.empty_like(verts)
         grad_tex = torch.empty_like(tex) if want_tex else None
+        grad_eyes = torch.empty_like(eyes) if want_eye else None      # camera optimisation (experiments/opt_camera.py:236)
         lib = _ext._lib.load()
         with _DeviceOf(verts.device):
             _ext._lib.check(lib.gendr_scene_backward(
                 verts.data_ptr(), int(verts_shared), index.data_ptr(), int(shared), tex.data_ptr(), eyes.data_ptr(), int(eyes_batched), camera, light,
                 soft_colors.data_ptr(), aggrs_info.data_ptr(), grad_images.data_ptr(), int(cfg.anti_aliasing), grad_vertices.data_ptr(),
-                grad_tex.data_ptr() if want_tex else None, B, V, F, T, cfg.params, workspace.data_ptr(), workspace.numel(),
-                _stream_of(verts.device)))
-        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, None, None, None, None
+                grad_tex.data_ptr() if want_tex else None, grad_eyes.data_ptr() if want_eye else None, B, V, F, T, cfg.params,
+                workspace.data_ptr(), workspace.numel(), _stream_of(verts.device)))
+        return grad_vertices.view(vshape), None, grad_tex.view(tshape) if want_tex else None, grad_eyes, None, None, None
 
 
 def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, image_size=256, background_color=[0, 0, 0],
@@ -449,7 +452,6 @@ def render_scene(vertices, faces, textures, eyes, camera=None, lighting=None, im
     light = make_light_params(**lighting) if lighting is not None else None
     if not torch.is_tensor(eyes):
         eyes = torch.tensor(eyes, dtype=torch.float32, device=vertices.device)
-    if eyes.requires_grad:
-        raise ValueError('render_scene does not differentiate w.r.t. the camera position: use LookAt/Look (torch path) for eyes that '
-                         'require a gradient (experiments/opt_camera.py)')
+    elif eyes.dtype is not torch.float32 or eyes.device != vertices.device:
+        eyes = eyes.to(device=vertices.device, dtype=torch.float32)      # differentiable: an eye that requires grad keeps its graph
     return GenDRSceneFunction.apply(vertices, faces, textures, eyes, cam, light, cfg)

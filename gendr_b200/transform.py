@@ -44,11 +44,11 @@ class _EyeCamera(Transform):
         if isinstance(eye, np.ndarray):
             eye = torch.from_numpy(eye)
         if torch.is_tensor(eye):
-            if eye.requires_grad or eye.ndimension() not in (1, 2) or eye.shape[-1] != 3:
-                return None                                  # camera optimisation (experiments/opt_camera.py): torch path
+            if eye.ndimension() not in (1, 2) or eye.shape[-1] != 3 or not eye.is_floating_point():
+                return None                                  # anything unusual: torch path
             if eye.ndimension() == 2 and eye.shape[0] != mesh.batch_size:
                 return None
-            return eye
+            return eye                                       # incl. eyes that require a gradient (experiments/opt_camera.py:236)
         if isinstance(eye, (list, tuple)) and len(eye) == 3 and all(isinstance(x, (int, float)) for x in eye):
             return eye
         return None
@@ -61,7 +61,7 @@ class _EyeCamera(Transform):
             # module must not reach the deferred step.
             cam = copy.copy(self)
             eye = self._eye
-            cam._eye = eye.detach().clone() if torch.is_tensor(eye) else copy.deepcopy(eye)
+            cam._eye = (eye.clone() if eye.requires_grad else eye.detach().clone()) if torch.is_tensor(eye) else copy.deepcopy(eye)
             if hasattr(cam, 'camera_direction'):
                 cam.camera_direction = copy.deepcopy(self.camera_direction)
             return Mesh(mesh._vertices, mesh.faces, mesh._textures, mesh.texture_res, mesh.texture_type,

@@ -143,9 +143,13 @@ typedef struct gendr_light_params {
 
 int gendr_camera_forward(const float* vertices, const float* eyes, int eyes_batched, float* screen_vertices, int batch,
                          int num_vertices, const gendr_camera_params* camera, void* stream);
-/* grad_vertices [B,V,3] is overwritten (no zero-fill needed) */
+/* grad_vertices [B,V,3] is overwritten (no zero-fill needed).  grad_eyes (may be NULL): gradient w.r.t. the camera position -- the
+ * optimisation target of /root/reference/experiments/opt_camera.py (eye with requires_grad, :236), which the reference gets from
+ * autograd through look_at() -- [B,3], or [3] summed over the batch when one eye is shared; eye_scratch: [B,12] floats of device
+ * scratch, required with grad_eyes (per-item accumulators, reduced by a second tiny kernel). */
 int gendr_camera_backward(const float* vertices, const float* eyes, int eyes_batched, const float* grad_screen_vertices,
-                          float* grad_vertices, int batch, int num_vertices, const gendr_camera_params* camera, void* stream);
+                          float* grad_vertices, float* grad_eyes, float* eye_scratch, int batch, int num_vertices,
+                          const gendr_camera_params* camera, void* stream);
 int gendr_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures,
                            float* lit_textures, int batch, int num_vertices, int num_faces, int texture_size,
                            const gendr_light_params* light, void* stream);
@@ -159,7 +163,8 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
  * Forward: camera kernel, lighting kernel, indexed face preprocessing, render kernel (4 launches; the reference issues ~40).
  * Backward: render backward (scatter-adds into the screen-space vertex gradient and the lit-texture gradient held in the
  * workspace), camera backward, lighting backward -> grad_vertices [B,V,3] w.r.t. the WORLD-space vertices and
- * grad_textures [B,F,T,3] w.r.t. the UNLIT textures (may be NULL).  light may be NULL (no lighting step).
+ * grad_textures [B,F,T,3] w.r.t. the UNLIT textures (may be NULL), grad_eyes w.r.t. the camera position(s) (may be NULL; see
+ * gendr_camera_backward).  light may be NULL (no lighting step).
  * pooled_colors / grad_is_pooled as in gendr_forward_render_aa.
  * vertices_shared != 0: ONE world-space mesh `vertices` [V,3] seen from `batch` eyes (the shared-mesh pattern of
  * experiments/opt_shape.py:86 without materialising vertices.repeat(batch,1,1)); gendr_scene_backward then returns the
@@ -175,8 +180,8 @@ int gendr_scene_backward(const float* vertices, int vertices_shared, const int* 
                          const float* eyes, int eyes_batched, const gendr_camera_params* camera,
                          const gendr_light_params* light, const float* soft_colors, const float* aggrs_info,
                          const float* grad_soft_colors, int grad_is_pooled, float* grad_vertices, float* grad_textures,
-                         int batch, int num_vertices, int num_faces, int texture_size, const gendr_render_params* params,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         float* grad_eyes, int batch, int num_vertices, int num_faces, int texture_size,
+                         const gendr_render_params* params, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Voxelizer: replaces gendr.functional.voxelization(faces, size, normalize=False)
  * (gendr/functional/voxelization.py:45-62) -- the pybind functions voxelize_sub1..4 of gendr/cuda/voxelization_cuda.cpp:85-88,

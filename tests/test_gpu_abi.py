@@ -113,8 +113,6 @@ def test_fused_paths_validate_face_indices():
     neg = faces.clone(); neg[1, 1] = -1
     with pytest.raises(IndexError):
         gd.functional.render_scene(v, neg.to(dev), tex, [0., 0., -3.], image_size=16)
-    with pytest.raises(ValueError):
-        gd.functional.render_scene(v, faces.to(dev), tex, torch.tensor([0., 0., -3.], device=dev, requires_grad=True), image_size=16)
 
 
 def test_batch_summed_backward_equals_sum_of_per_item_gradients():
