@@ -430,6 +430,35 @@ def test_reference_cuda_axes_full_size(reference_cuda, c5_mesh, dist, dkw, tcn, 
     assert not failures, '\n'.join(failures)
 
 
+@pytest.mark.parametrize('which', ['c2', 'c3', 'c4'])
+def test_not_less_accurate_than_the_reference(reference_cuda, which):
+    """SURVEY 8(d) context numbers as an assertion: against the reference's own <double> instantiation (its pybind functions called
+    with fp64 buffers, K.cu:1099) our fp32 gradients are as accurate as the reference's fp32 gradients.  This is what backs the
+    approximate divisions / ex2.approx in gradient-only terms of the backward kernels: they must not cost accuracy
+    that the reference has.  (Images are not compared here: both fp32 implementations differ from <double> by up to O(1) on sliver
+    faces in exactly the same way)"""
+    from ref_gpu import reference_render_raw
+    dev = _dev()
+    fv, ft, cfg = {'c2': scenes.config_c2, 'c3': scenes.config_c3, 'c4': scenes.config_c4}[which](batch=2)
+    fv, ft = scenes.with_sentinel(fv, ft)
+    kw = dict(double_side=False, **cfg)
+    g = torch.randn(2, 4, 256, 256, generator=torch.Generator().manual_seed(2))
+    _, gf, gt = render_new(fv, ft, g, dev, **kw)
+    a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
+    reference_render(reference_cuda, a, b, **kw).backward(g.to(dev))
+    _, gf64, gt64 = reference_render_raw(reference_cuda, fv.to(dev), ft.to(dev), g.to(dev), torch.float64, **kw)
+    for name, ours, ref32, ref64 in (('grad_faces', gf, a.grad, gf64), ('grad_textures', gt, b.grad, gt64)):
+        scale = float(ref64.abs().max())
+        e_ours = (ours.double() - ref64).abs()
+        e_ref = (ref32.double() - ref64).abs()
+        # where the two fp32 results agree (to 1e-4 of the maximum) they are equally far from <double>; compare the error there ...
+        agree = (ours.double() - ref32.double()).abs() <= 1e-4 * scale
+        assert float(agree.double().mean()) >= 0.9999, (which, name)
+        # ... as a mean (systematic loss of accuracy would show up here) and at the maximum
+        assert float(e_ours[agree].mean()) <= 1.02 * float(e_ref[agree].mean()) + 1e-9 * scale, (which, name, float(e_ours[agree].mean()), float(e_ref[agree].mean()))
+        assert float(e_ours[agree].max()) <= float(e_ref[agree].max()) + 1e-4 * scale, (which, name)
+
+
 def test_reference_cuda_c2_scaled_views(reference_cuda):
     """C2 mesh with the paper-tuned scale of logistic + probabilistic (10^-2.0 is the default; 10^-1.5 widens every face's
     footprint ~3x) and anti-aliasing through the module API -- the configuration experiments/opt_shape.py runs."""

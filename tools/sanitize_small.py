@@ -20,3 +20,12 @@ a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
 img = gd.functional.render(a, b, image_size=37, dist_func='logistic', dist_scale=0.05)
 img.backward(torch.ones_like(img)); torch.cuda.synchronize()
 print('multiwave', float(img.sum()))
+# fused scene path: camera + lighting kernels, shared-mesh batch-summed gradient, gradient w.r.t. the eye (two launches)
+verts, faces = scenes.icosphere(1)
+v = (verts * 0.5).to(dev).requires_grad_(True)
+eyes = scenes.orbit_eyes(3).to(dev).requires_grad_(True)
+tex = torch.rand(3, faces.shape[0], 1, 3).to(dev).requires_grad_(True)
+img = gd.functional.render_scene(v, faces.to(dev), tex, eyes, camera=dict(viewing_angle=15.), lighting={}, image_size=48, dist_func='logistic',
+                                 dist_scale=0.03, anti_aliasing=True)
+img.backward(torch.ones_like(img)); torch.cuda.synchronize()
+print('scene', float(img.sum()), float(v.grad.abs().sum()), float(eyes.grad.abs().sum()))
