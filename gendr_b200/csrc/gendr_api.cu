@@ -137,23 +137,18 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
     P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
-    P.super_chunk = F < 2048 ? ((F + 255) / 256) * 256 : 2048;     // index list of 4 KB next to the wave buffers: 4 CTAs/SM
-    if (P.super_chunk < 256) P.super_chunk = 256;
     return 0;
 }
 
-static size_t smem_bytes(const RenderParams& P, bool face_stationary_backward) {
-    const int n_sc = P.super_chunk;
-    const int Fw = ((n_sc + NWARPS - 1) / NWARPS + 31) & ~31;
-    const size_t fixed = face_stationary_backward ? smem_fixed_bytes<BWD_WAVE, NPIX_BWD>() : smem_fixed_bytes<WAVE_FACES, 0>();
-    return fixed + (size_t)NWARPS * Fw * 2;
+static size_t smem_bytes(const RenderParams&, bool face_stationary_backward) {
+    return face_stationary_backward ? smem_bytes_total<BWD_WAVE, NPIX_BWD>() : smem_bytes_total<WAVE_FACES, 0>();
 }
 
-// Backward kernel choice by measured density regime.  Face-stationary (one reduction per face per CTA, pixel state in shared
-// memory) wins when most staged faces reach most blocks of a tile -- heavy-tailed distributions, wide dist_scale: measured C4
-// 103 vs 112 ms at B = 16 -- pixel-stationary (pixel state in registers, one reduction per face per warp) when faces touch only
-// a few blocks -- C3: 5.97 vs 6.38 ms at B = 64.  The switch is the distribution's cull distance in pixels (>= 2 tiles => dense).
-// GENDR_B200_BWD=ps|fs forces one of them (A/B measurements).
+// Backward kernel choice.  The face-stationary kernel (one reduction per face per CTA, pixel state in shared memory, faces dealt
+// round-robin to the warps) is the backward pass: measured on this round's final kernels it wins or ties in every regime --
+// C4 (dense) 52.1 vs 58.7 ms at B = 8, C3 (sparse) 5.74 vs 5.86 ms at B = 64, C2 0.75 vs 0.76 ms (profiles/r2_kernel_ab_timings.jsonl).
+// The pixel-stationary variant (pixel state in registers, one reduction per face per WARP) stays compiled for A/B measurements:
+// GENDR_B200_BWD=ps selects it.
 static int forced_backward_mode() {
     static const int forced = [] {
         const char* e = getenv("GENDR_B200_BWD");
@@ -161,11 +156,9 @@ static int forced_backward_mode() {
     }();
     return forced;
 }
-static int backward_mode(const RenderParams& P) {
+static int backward_mode(const RenderParams&) {
     const int forced = forced_backward_mode();
-    if (forced >= 0) return forced;
-    const float reach_px = fminf(P.cull_radius, P.sqrt_thr) * 0.5f * (float)P.S;      // NaN / INF compare false => dense
-    return (reach_px < 2.f * TILE_W) ? 1 : 0;
+    return forced >= 0 ? forced : 0;
 }
 
 struct DeviceScope {   // run on the device that owns the data, restore the caller's device afterwards
