@@ -11,10 +11,25 @@ cached C parameter struct, three torch.empty, one ctypes call, one autograd node
 cached configuration object, so autograd neither wraps nor returns 19 Nones) -- no clones, no dtype/contiguity conversions unless
 the caller's tensors need them, no device-guard when the tensors already live on the current device.
 """
+import ctypes as _ctypes
+import os as _os
+
 import torch
 from torch.autograd import Function
 
 from ..cuda import generalized_renderer as _ext
+
+# The autograd node of render() in C++ (gendr_b200/csrc/torch_binding.cpp -> gendr_b200/_torchbind*.so): same C-ABI calls, no
+# interpreter on the forward/backward path.  Optional: without it (not built, or an alternative library selected through
+# GENDR_B200_LIB) render() uses the Python node below.  GENDR_B200_TORCHBIND=0 disables it (A/B measurements).
+_tb = None
+if _os.environ.get('GENDR_B200_TORCHBIND', '1') != '0' and not _os.environ.get('GENDR_B200_LIB'):
+    try:
+        from .. import _torchbind as _tb
+        if _tb.params_size() != _ctypes.sizeof(_ext._lib.RenderParams):
+            _tb = None
+    except Exception:      # not built
+        _tb = None
 
 # name -> id maps of the reference (functional/renderer.py:44-83)
 DIST_FUNC_IDS = {
@@ -40,7 +55,7 @@ def _resolve(value, table):
 
 class _Config(object):
     """One render configuration: the C parameter struct + the flags the host side needs.  Cached per distinct argument tuple."""
-    __slots__ = ('params', 'image_size', 'anti_aliasing')
+    __slots__ = ('params', 'params_addr', 'image_size', 'anti_aliasing')
 
 
 _CONFIG_CACHE = {}
@@ -65,6 +80,7 @@ def _config(image_size, background_color, dist_func, dist_scale, dist_squared, d
             _resolve(aggr_rgb_func, AGGR_RGB_FUNC_IDS), aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side,
             TEXTURE_TYPE_IDS[texture_type], background_color)
         cfg.image_size, cfg.anti_aliasing = int(image_size), bool(anti_aliasing)
+        cfg.params_addr = _ctypes.addressof(cfg.params)
         if key is not None:
             if len(_CONFIG_CACHE) > 512:
                 _CONFIG_CACHE.clear()
@@ -314,6 +330,8 @@ def render(face_vertices, textures, image_size=256, background_color=[0, 0, 0],
     [B,4,S/2,S/2] -- F.avg_pool2d(render(...), 2, 2) of gendr/renderer.py:92-93, fused into the kernels (bit-identical)."""
     cfg = _config(image_size, background_color, dist_func, dist_scale, dist_squared, dist_shape, dist_shift, dist_eps, aggr_alpha_func,
                   aggr_alpha_t_conorm_p, aggr_rgb_func, aggr_rgb_eps, aggr_rgb_gamma, near, far, double_side, texture_type, anti_aliasing)
+    if _tb is not None:
+        return _tb.render_faces(face_vertices, textures, cfg.params_addr, cfg.anti_aliasing)      # the struct is copied by the node
     return _RenderFaces.apply(face_vertices, textures, cfg)
 
 

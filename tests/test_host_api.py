@@ -193,3 +193,17 @@ def test_bench_reference_arm_contract_on_cpu():
         assert key in d, key
     assert d['impl'] == 'reference' and d['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 0
     assert d['cpu_baseline']['kind'] in ('reference', 'port') and 'workload' in d['config']
+
+
+def test_cpp_autograd_node_is_built_and_consistent():
+    """gendr_b200/_torchbind (csrc/torch_binding.cpp): the C++ autograd node of functional.render.  Host code over the same C ABI;
+    its parameter struct must be the header's, and it must refuse CPU tensors like the Python node (no fallback)."""
+    import glob
+    if not glob.glob(os.path.join(ROOT, 'gendr_b200', '_torchbind*.so')):
+        pytest.skip('gendr_b200/_torchbind not built (make -C gendr_b200/csrc torchbind)')
+    from gendr_b200 import _torchbind
+    assert _torchbind.params_size() == C.sizeof(_lib.RenderParams)
+    p = _lib.RenderParams()
+    p.image_size = 8
+    with pytest.raises(TypeError):
+        _torchbind.render_faces(torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 1, 3), C.addressof(p), False)
