@@ -65,6 +65,15 @@ __global__ void __launch_bounds__(256) prep_indexed_kernel(const __grid_constant
     rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
 }
 
+// zero-fill of the two gradient buffers of a backward call in ONE launch (two cudaMemsetAsync cost two launches; tiny scenes are
+// launch bound).  n_a / n_b in floats; either buffer may be null.
+__global__ void __launch_bounds__(256) zero2_kernel(float* __restrict__ a, long long n_a, float* __restrict__ b, long long n_b) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_a + n_b; i += stride) {
+        if (i < n_a) a[i] = 0.f; else b[i - n_a] = 0.f;
+    }
+}
+
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
@@ -182,6 +191,24 @@ static uint2* ws_rects(void* ws, int B, int F) {
     return reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + rec_bytes);
 }
 
+static int zero_grads2(float* a, long long n_a, float* b, long long n_b, cudaStream_t st) {
+    if (!a) n_a = 0;
+    if (!b) n_b = 0;
+    const long long n = n_a + n_b;
+    if (n == 0) return 0;
+    if (n > (1ll << 20) || n_a == 0 || n_b == 0) {      // large (or single) buffers: the copy engine's memset is the right tool
+        if (n_a) GENDR_CUDA(cudaMemsetAsync(a, 0, (size_t)n_a * sizeof(float), st), "zero gradient buffer");
+        if (n_b) GENDR_CUDA(cudaMemsetAsync(b, 0, (size_t)n_b * sizeof(float), st), "zero gradient buffer");
+        return 0;
+    }
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    zero2_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, n_a, b, n_b);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "zero2_kernel launch");
+    return 0;
+}
+
 static int run_prep(const RenderParams& P, const float* faces, float* faces_info, void* ws, cudaStream_t st) {
     const long long n = (long long)P.B * P.F;
     if (n == 0) return 0;
@@ -195,6 +222,8 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     if (P.B == 0) return 0;
     LaunchCfg cfg;
     cfg.grid = dim3((unsigned)(P.B * P.tiles_x * P.tiles_y));
+    cfg.device = 0;
+    (void)cudaGetDevice(&cfg.device);
     cfg.bwd_mode = backward ? backward_mode(P) : 0;
     if (backward && forced_backward_mode() < 0) {
         // small problems: fewer CTAs than ~two waves of the machine (148 SMs x 4 CTAs).  The face-stationary kernel then also
@@ -363,8 +392,7 @@ static int gendr_backward_render_chunk(const float* faces, const float* textures
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_render_forward_backward_host");
     (void)workspace_bytes; (void)faces;
-    GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
-    if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
+    if (int e = zero_grads2(grad_faces, (long long)batch * num_faces * 9, grad_textures, (long long)batch * num_faces * texture_size * 3, st)) return e;
     KernelIO io;
     memset(&io, 0, sizeof io);
     io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
@@ -409,10 +437,8 @@ static int backward_render_impl(const char* who, bool batchsum, const float* fac
     GENDR_CUDA(dev.enter(faces), "selecting the device that owns `faces`");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (!workspace_valid) if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
-    if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)(batchsum ? 1 : batch) * num_faces * 9 * sizeof(float), st), "zero grad_faces");
-        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
-    }
+    if (zero_grads) if (int e = zero_grads2(grad_faces, (long long)(batchsum ? 1 : batch) * num_faces * 9, grad_textures,
+                                            (long long)batch * num_faces * texture_size * 3, st)) return e;
     KernelIO io;
     memset(&io, 0, sizeof io);
     io.records = ws_records(workspace); io.rects = ws_rects(workspace, batch, num_faces);
@@ -561,8 +587,7 @@ static int backward_indexed_impl(const RenderParams& P, const int* face_index, i
                                  const float* aggrs_info, float* grad_vertices, float* grad_textures, const float* grad_soft_colors,
                                  int grad_is_pooled, int num_vertices, int zero_grads, void* workspace, cudaStream_t st, bool batchsum = false) {
     if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)(batchsum ? 1 : P.B) * num_vertices * 3 * sizeof(float), st), "zero grad_vertices");
-        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)P.B * P.F * P.T * 3 * sizeof(float), st), "zero grad_textures");
+        if (int e = zero_grads2(grad_vertices, (long long)(batchsum ? 1 : P.B) * num_vertices * 3, grad_textures, (long long)P.B * P.F * P.T * 3, st)) return e;
     }
     KernelIO io;
     memset(&io, 0, sizeof io);
@@ -664,8 +689,7 @@ int gendr_backward_render_aa(const float* faces, const float* textures, const fl
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (!workspace_valid) if (int e = run_prep(P, faces, nullptr, workspace, st)) return e;
     if (zero_grads) {
-        GENDR_CUDA(cudaMemsetAsync(grad_faces, 0, (size_t)batch * num_faces * 9 * sizeof(float), st), "zero grad_faces");
-        if (grad_textures) GENDR_CUDA(cudaMemsetAsync(grad_textures, 0, (size_t)batch * num_faces * texture_size * 3 * sizeof(float), st), "zero grad_textures");
+        if (int e = zero_grads2(grad_faces, (long long)batch * num_faces * 9, grad_textures, (long long)batch * num_faces * texture_size * 3, st)) return e;
     }
     KernelIO io;
     memset(&io, 0, sizeof io);
@@ -874,8 +898,7 @@ int gendr_scene_backward(const float* vertices, int vertices_shared, const int* 
     // the rasterizer's texture gradient: w.r.t. the LIT textures when lighting is on (always needed then: it also feeds the
     // normals' gradient), else straight into the caller's grad_textures
     float* g_tex = light ? w.grad_lit : grad_textures;
-    GENDR_CUDA(cudaMemsetAsync(w.grad_screen, 0, (size_t)batch * num_vertices * 12, st), "zero screen-space vertex gradient");
-    if (g_tex) GENDR_CUDA(cudaMemsetAsync(g_tex, 0, (size_t)batch * num_faces * texture_size * 12, st), "zero texture gradient");
+    if (int e = zero_grads2(w.grad_screen, (long long)batch * num_vertices * 3, g_tex, (long long)batch * num_faces * texture_size * 3, st)) return e;
     if (int e = backward_indexed_impl(P, face_index, index_shared, light ? w.lit : textures, soft_colors, aggrs_info, w.grad_screen, g_tex,
                                       grad_soft_colors, grad_is_pooled, num_vertices, 0, w.render, st)) return e;
     const long long vstride = vertices_shared ? 0 : (long long)num_vertices * 3;
