@@ -459,6 +459,16 @@ def test_not_less_accurate_than_the_reference(reference_cuda, which):
         assert float(e_ours[agree].max()) <= float(e_ref[agree].max()) + 1e-4 * scale, (which, name)
 
 
+def test_reference_cuda_more_than_65535_faces(reference_cuda):
+    """70 000 faces: the tile scan's survivor list holds 16-bit face indices RELATIVE to the start of the current list and is flushed
+    before they could overflow (scan_chunk_append / the flush rule in the kernels) -- sparse (logistic) and dense (cauchy) regimes."""
+    dev = _dev()
+    fv, ft = scenes.soup(70000, batch=1, seed=13, size=0.01)
+    for kw in (dict(image_size=64, dist_func='logistic', aggr_alpha_func='probabilistic', dist_scale=0.004, double_side=True),
+               dict(image_size=32, dist_func='cauchy', aggr_alpha_func='probabilistic', dist_scale=0.002, double_side=True)):
+        _vs_reference(reference_cuda, '70k faces/' + kw['dist_func'], fv, ft, dev, **kw)
+
+
 def test_reference_cuda_c2_scaled_views(reference_cuda):
     """C2 mesh with the paper-tuned scale of logistic + probabilistic (10^-2.0 is the default; 10^-1.5 widens every face's
     footprint ~3x) and anti-aliasing through the module API -- the configuration experiments/opt_shape.py runs."""
