@@ -145,6 +145,9 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.gamma_kummer0 = (float)(1. / std::tgamma((double)u->dist_shape + 1.));
     P.gamma_lcoef = (float)((double)u->dist_shape * std::log(1. / (double)u->dist_scale) - std::lgamma((double)u->dist_shape));
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
+    P.zrange = P.far_ - P.near_;                         // fp32 subtraction, as the kernels' gd_sub(far, near) was
+    P.y_tau = 1.0f / P.dist_scale; P.y_gamma = 1.0f / P.rgb_gamma; P.y_zrange = 1.0f / P.zrange;      // IEEE: correctly rounded
+    P.consts_ok = (rcp_in_range(P.dist_scale) && rcp_in_range(P.rgb_gamma) && rcp_in_range(P.zrange)) ? 1 : 0;
     P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
     return 0;
 }
@@ -335,6 +338,9 @@ __global__ void division_selftest_kernel(unsigned long long n, unsigned long lon
         const Rcp r = make_rcp(b);
         const float q1 = div_exact(a, r), q2 = __fdiv_rn(a, b);
         if (__float_as_uint(q1) != __float_as_uint(q2)) ++bad;
+        Rcp rr = r;                       // the flavour used for the launch constants: y = RN(1 / b), formed on the host
+        rr.y = __frcp_rn(b);
+        if (__float_as_uint(div_exact(a, rr)) != __float_as_uint(q2)) ++bad;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
