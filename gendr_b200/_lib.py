@@ -54,6 +54,8 @@ SIGNATURES = {
     'gendr_camera_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _PC, _P]),
     'gendr_lighting_forward': (_I, [_P, _P, _I, _P, _P, _I, _I, _I, _I, _PL, _P]),
     'gendr_lighting_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _PL, _P]),
+    'gendr_vertex_lighting_forward': (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _PL, _P]),
+    'gendr_vertex_lighting_backward': (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _PL, _P]),
     'gendr_scene_workspace_bytes': (_SZ, [_I, _I, _I, _I]),
     'gendr_scene_forward': (_I, [_P, _I, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),
     'gendr_scene_backward': (_I, [_P, _I, _P, _I, _P, _P, _I, _PC, _PL, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _PP, _P, _SZ, _P]),

@@ -829,6 +829,60 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
                                   num_vertices, num_faces, texture_size, reinterpret_cast<cudaStream_t>(stream));
 }
 
+// Lighting of VERTEX textures (gendr/lighting.py:60-66): two launches forward (corner cross products summed per vertex, then the
+// per-vertex light), two backward.  normal_sums [B,V,3] is written by the forward call and read by the backward call.
+int gendr_vertex_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures, float* lit_textures,
+                                  float* normal_sums, int batch, int num_vertices, int num_faces, const gendr_light_params* light, void* stream) {
+    if (!light || batch < 0 || num_faces < 0 || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_vertex_lighting_forward");
+    if (batch == 0) return 0;
+    if (!vertices || (!face_index && num_faces > 0) || !textures || !lit_textures || !normal_sums)
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_vertex_lighting_forward");
+    LightParams L;
+    make_light(L, light);
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long nv = (long long)batch * num_vertices, nf = (long long)batch * num_faces;
+    GENDR_CUDA(cudaMemsetAsync(normal_sums, 0, (size_t)nv * 12, st), "clearing the vertex normal sums");
+    if (nf > 0) {
+        vertex_normal_sums_kernel<<<blocks_for(nf), 256, 0, st>>>(vertices, face_index, index_shared ? 0 : (long long)num_faces * 3, normal_sums, batch,
+                                                                  num_vertices, num_faces);
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "vertex_normal_sums_kernel launch");
+    }
+    vertex_lighting_forward_kernel<<<blocks_for(nv), 256, 0, st>>>(L, normal_sums, textures, lit_textures, nv);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "vertex_lighting_forward_kernel launch");
+    return 0;
+}
+
+int gendr_vertex_lighting_backward(const float* vertices, const int* face_index, int index_shared, const float* textures, const float* normal_sums,
+                                   const float* grad_lit_textures, float* grad_textures, float* grad_vertices, float* grad_sums_scratch, int batch,
+                                   int num_vertices, int num_faces, const gendr_light_params* light, void* stream) {
+    if (!light || batch < 0 || num_faces < 0 || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "invalid argument to gendr_vertex_lighting_backward");
+    if (batch == 0) return 0;
+    if (!vertices || (!face_index && num_faces > 0) || !textures || !normal_sums || !grad_lit_textures || (grad_vertices && !grad_sums_scratch))
+        return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_vertex_lighting_backward");
+    LightParams L;
+    make_light(L, light);
+    DeviceScope dev;
+    GENDR_CUDA(dev.enter(vertices), "selecting the device that owns `vertices`");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const long long nv = (long long)batch * num_vertices, nf = (long long)batch * num_faces;
+    if (!grad_textures && !grad_vertices) return 0;
+    vertex_lighting_backward_kernel<<<blocks_for(nv), 256, 0, st>>>(L, normal_sums, textures, grad_lit_textures, grad_textures,
+                                                                    grad_vertices ? grad_sums_scratch : nullptr, nv);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "vertex_lighting_backward_kernel launch");
+    if (grad_vertices && nf > 0) {
+        vertex_normal_sums_backward_kernel<<<blocks_for(nf), 256, 0, st>>>(vertices, face_index, index_shared ? 0 : (long long)num_faces * 3, grad_sums_scratch,
+                                                                           grad_vertices, batch, num_vertices, num_faces);
+        g_launches++;
+        GENDR_CUDA(cudaGetLastError(), "vertex_normal_sums_backward_kernel launch");
+    }
+    return 0;
+}
+
 // scene workspace: [render workspace | screen vertices B*V*3 | grad screen vertices B*V*3 | lit textures B*F*T*3 | grad lit B*F*T*3 |
 //                   eye-gradient accumulators B*12]
 struct SceneWs { void* render; float* screen; float* grad_screen; float* lit; float* grad_lit; float* eye_acc; };

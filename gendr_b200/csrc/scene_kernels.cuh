@@ -2,7 +2,8 @@
 //
 //   camera transform    look_at / look  +  perspective / orthogonal
 //                       (/root/reference/gendr/functional/look_at.py:11-68, look.py:11-56, gendr/transform.py:14-44,109-168)
-//   lighting            ambient + one directional light folded into surface textures
+//   lighting            ambient + one directional light folded into surface textures (per face) or vertex textures (per vertex,
+//                       vertex normals = gendr/functional/vertex_normals.py)
 //                       (/root/reference/gendr/lighting.py:37-71, gendr/functional/lighting.py:12-48,
 //                        surface normals gendr/mesh.py:104-108)
 //   and their backward passes (the reference gets those from autograd over ~30 small torch kernels).
@@ -287,6 +288,111 @@ __global__ void __launch_bounds__(256) lighting_backward_kernel(const __grid_con
     atomicAdd(gv + (size_t)i0 * 3 + 0, ge.x); atomicAdd(gv + (size_t)i0 * 3 + 1, ge.y); atomicAdd(gv + (size_t)i0 * 3 + 2, ge.z);
     atomicAdd(gv + (size_t)i1 * 3 + 0, -(ga.x + ge.x)); atomicAdd(gv + (size_t)i1 * 3 + 1, -(ga.y + ge.y));
     atomicAdd(gv + (size_t)i1 * 3 + 2, -(ga.z + ge.z));
+}
+
+// ---- lighting of vertex textures ------------------------------------------------------------------------------------
+// gendr/lighting.py:60-66 with mesh.vertex_normals = gendr/functional/vertex_normals.py:11-49: every face adds the (un-normalised)
+// cross product taken at each of its corners to that corner's vertex (three index_add_ calls = atomics in arbitrary order there
+// as here), the sums are F.normalize'd, and the vertex colour is multiplied by ambient + directional light.
+// normal_sums [B,V,3] is scratch the caller zero-fills (the API entry does); it is kept for the backward pass.
+__device__ __forceinline__ void atomic_add3(float* p, f3 v) { atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); }
+
+__global__ void __launch_bounds__(256) vertex_normal_sums_kernel(const float* __restrict__ vertices, const int* __restrict__ face_index,
+                                                                 long long index_batch_stride, float* __restrict__ normal_sums, int B, int V,
+                                                                 int F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const long long b = i / F, f = i - b * F;
+    const int* idx = face_index + b * index_batch_stride + f * 3;
+    const int i0 = clamp_index(__ldg(idx + 0), V), i1 = clamp_index(__ldg(idx + 1), V), i2 = clamp_index(__ldg(idx + 2), V);
+    const float* vb = vertices + b * (long long)V * 3;
+    const f3 v0 = load3(vb + (size_t)i0 * 3), v1 = load3(vb + (size_t)i1 * 3), v2 = load3(vb + (size_t)i2 * 3);
+    float* nb = normal_sums + b * (long long)V * 3;
+    atomic_add3(nb + (size_t)i1 * 3, cross3(sub3(v2, v1), sub3(v0, v1)));      // vertex_normals.py:33-35
+    atomic_add3(nb + (size_t)i2 * 3, cross3(sub3(v0, v2), sub3(v1, v2)));      // :36-38
+    atomic_add3(nb + (size_t)i0 * 3, cross3(sub3(v1, v0), sub3(v2, v0)));      // :39-41
+}
+
+__device__ __forceinline__ void vertex_light(const LightParams& L, f3 s, float light[3], f3* n_out = nullptr, float* norm_out = nullptr,
+                                             float* cos_out = nullptr) {
+    float norm;
+    const f3 n = normalize3(s, 1e-6f, &norm);                                                      // vertex_normals.py:43
+    const float c = sum3_torch(__fmul_rn(n.x, L.direction[0]), __fmul_rn(n.y, L.direction[1]), __fmul_rn(n.z, L.direction[2]));
+    const float cosine = fmaxf(c, 0.f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) light[k] = __fadd_rn(L.ambient[k], __fmul_rn(L.intensity_dir, __fmul_rn(L.color_dir[k], cosine)));
+    if (n_out) *n_out = n;
+    if (norm_out) *norm_out = norm;
+    if (cos_out) *cos_out = c;
+}
+
+// lit[b,v,:] = textures[b,v,:] * light(b,v)      (lighting.py:66)
+__global__ void __launch_bounds__(256) vertex_lighting_forward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ normal_sums,
+                                                                      const float* __restrict__ textures, float* __restrict__ lit, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float light[3];
+    vertex_light(L, load3(normal_sums + i * 3), light);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lit[i * 3 + k] = __fmul_rn(__ldg(textures + i * 3 + k), light[k]);
+}
+
+// backward, vertex part: grad_lit [B,V,3] -> grad_textures (store; may be null) and grad_sums [B,V,3] = d loss / d normal_sums (store)
+__global__ void __launch_bounds__(256) vertex_lighting_backward_kernel(const __grid_constant__ LightParams L, const float* __restrict__ normal_sums,
+                                                                       const float* __restrict__ textures, const float* __restrict__ grad_lit,
+                                                                       float* __restrict__ grad_textures, float* __restrict__ grad_sums, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float light[3], norm, c;
+    f3 nrm;
+    vertex_light(L, load3(normal_sums + i * 3), light, &nrm, &norm, &c);
+    float G[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float g = __ldg(grad_lit + i * 3 + k);
+        G[k] = g * __ldg(textures + i * 3 + k);
+        if (grad_textures) grad_textures[i * 3 + k] = g * light[k];
+    }
+    if (!grad_sums) return;
+    f3 gs = mk3(0.f, 0.f, 0.f);
+    if (c > 0.f) {                                                    // relu
+        const float gcos = L.intensity_dir * (L.color_dir[0] * G[0] + L.color_dir[1] * G[1] + L.color_dir[2] * G[2]);
+        const f3 gn = mk3(gcos * L.direction[0], gcos * L.direction[1], gcos * L.direction[2]);
+        if (norm > 1e-6f) gs = scale3(sub3(gn, scale3(nrm, dot3(nrm, gn))), 1.f / norm);
+        else gs = scale3(gn, 1e6f);
+    }
+    grad_sums[i * 3 + 0] = gs.x; grad_sums[i * 3 + 1] = gs.y; grad_sums[i * 3 + 2] = gs.z;
+}
+
+// backward, face part: the three corner cross products of every face -> atomic adds into grad_vertices [B,V,3]
+__global__ void __launch_bounds__(256) vertex_normal_sums_backward_kernel(const float* __restrict__ vertices, const int* __restrict__ face_index,
+                                                                          long long index_batch_stride, const float* __restrict__ grad_sums,
+                                                                          float* __restrict__ grad_vertices, int B, int V, int F) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F) return;
+    const long long b = i / F, f = i - b * F;
+    const int* idx = face_index + b * index_batch_stride + f * 3;
+    const int i0 = clamp_index(__ldg(idx + 0), V), i1 = clamp_index(__ldg(idx + 1), V), i2 = clamp_index(__ldg(idx + 2), V);
+    const float* vb = vertices + b * (long long)V * 3;
+    const float* gb = grad_sums + b * (long long)V * 3;
+    const f3 v0 = load3(vb + (size_t)i0 * 3), v1 = load3(vb + (size_t)i1 * 3), v2 = load3(vb + (size_t)i2 * 3);
+    const f3 g0 = load3(gb + (size_t)i0 * 3), g1 = load3(gb + (size_t)i1 * 3), g2 = load3(gb + (size_t)i2 * 3);
+    // c = a x e  =>  d/da = e x gc,  d/de = gc x a
+    f3 d0 = mk3(0.f, 0.f, 0.f), d1 = d0, d2 = d0;
+    {   // at v1: a = v2 - v1, e = v0 - v1
+        const f3 a = sub3(v2, v1), e = sub3(v0, v1), ga = cross3(e, g1), ge = cross3(g1, a);
+        d2 = add3(d2, ga); d0 = add3(d0, ge); d1 = sub3(d1, add3(ga, ge));
+    }
+    {   // at v2: a = v0 - v2, e = v1 - v2
+        const f3 a = sub3(v0, v2), e = sub3(v1, v2), ga = cross3(e, g2), ge = cross3(g2, a);
+        d0 = add3(d0, ga); d1 = add3(d1, ge); d2 = sub3(d2, add3(ga, ge));
+    }
+    {   // at v0: a = v1 - v0, e = v2 - v0
+        const f3 a = sub3(v1, v0), e = sub3(v2, v0), ga = cross3(e, g0), ge = cross3(g0, a);
+        d1 = add3(d1, ga); d2 = add3(d2, ge); d0 = sub3(d0, add3(ga, ge));
+    }
+    float* gv = grad_vertices + b * (long long)V * 3;
+    atomic_add3(gv + (size_t)i0 * 3, d0); atomic_add3(gv + (size_t)i1 * 3, d1); atomic_add3(gv + (size_t)i2 * 3, d2);
 }
 
 }  // namespace gendr

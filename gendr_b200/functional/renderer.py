@@ -376,6 +376,54 @@ def make_light_params(intensity_ambient=0.5, color_ambient=(1, 1, 1), intensity_
     return p
 
 
+class VertexLightingFunction(Function):
+    """textures [B,V,3] * (ambient + directional light from the vertex normals): gendr.Lighting.forward for texture_type='vertex'
+    (gendr/lighting.py:60-66, vertex normals gendr/functional/vertex_normals.py:11-49) as two launches forward and two backward
+    (gendr_vertex_lighting_*); gradients w.r.t. the vertices (through the normals) and the unlit textures."""
+    @staticmethod
+    def forward(ctx, vertices, faces, textures, light):
+        if not vertices.is_cuda:
+            raise TypeError('GenDR only supports CUDA Tensors.')
+        verts = _f32c(vertices)
+        dev = verts.device
+        B, V = verts.shape[0], verts.shape[1]
+        check_face_indices(faces, V)
+        index = _index_i32(faces, dev)
+        tex = _f32c(textures, dev)
+        if tuple(tex.shape) != (B, V, 3):
+            raise ValueError('vertex textures must be [batch, num_vertices, 3]')
+        lit, sums = torch.empty_like(tex), torch.empty_like(verts)
+        lib = _ext._lib.load()
+        with _DeviceOf(dev):
+            _ext._lib.check(lib.gendr_vertex_lighting_forward(verts.data_ptr(), index.data_ptr(), int(index.ndimension() == 2), tex.data_ptr(),
+                                                              lit.data_ptr(), sums.data_ptr(), B, V, index.shape[-2], light, _stream_of(dev)))
+        ctx.light = light
+        ctx.save_for_backward(verts, index, tex, sums)
+        return lit
+
+    @staticmethod
+    def backward(ctx, grad_lit):
+        verts, index, tex, sums = ctx.saved_tensors
+        B, V = verts.shape[0], verts.shape[1]
+        grad_lit = _f32c(grad_lit)
+        want_v, want_t = ctx.needs_input_grad[0], ctx.needs_input_grad[2]
+        grad_v = torch.zeros_like(verts) if want_v else None
+        scratch = torch.empty_like(verts) if want_v else None
+        grad_t = torch.empty_like(tex) if want_t else None
+        lib = _ext._lib.load()
+        with _DeviceOf(verts.device):
+            _ext._lib.check(lib.gendr_vertex_lighting_backward(
+                verts.data_ptr(), index.data_ptr(), int(index.ndimension() == 2), tex.data_ptr(), sums.data_ptr(), grad_lit.data_ptr(),
+                grad_t.data_ptr() if want_t else None, grad_v.data_ptr() if want_v else None, scratch.data_ptr() if want_v else None,
+                B, V, index.shape[-2], ctx.light, _stream_of(verts.device)))
+        return grad_v, None, grad_t, None
+
+
+def vertex_lighting(vertices, faces, textures, **lighting):
+    """Lit vertex textures [B,V,3]; keyword arguments of make_light_params."""
+    return VertexLightingFunction.apply(vertices, faces, textures, make_light_params(**lighting))
+
+
 _SCENE_WS_BYTES = {}
 
 

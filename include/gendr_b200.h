@@ -158,6 +158,20 @@ int gendr_lighting_backward(const float* vertices, const int* face_index, int in
                             const float* grad_lit_textures, float* grad_textures, float* grad_vertices, int batch,
                             int num_vertices, int num_faces, int texture_size, const gendr_light_params* light, void* stream);
 
+/* Lighting of VERTEX textures: replaces gendr.Lighting.forward for texture_type == 'vertex' (gendr/lighting.py:60-66) together with
+ * the vertex normals it reads (Mesh.vertex_normals = gendr/functional/vertex_normals.py:11-49: per-corner cross products summed per
+ * vertex by index_add_, then F.normalize) and what autograd derives for them.  textures / lit_textures [B,V,3].
+ * normal_sums [B,V,3]: written by the forward call (zero-filled inside), read by the backward call.
+ * Backward: grad_textures [B,V,3] is overwritten (may be NULL); the normals' gradient is ADDED to grad_vertices [B,V,3] (may be
+ * NULL; otherwise grad_sums_scratch [B,V,3] floats of device scratch is required). */
+int gendr_vertex_lighting_forward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                  float* lit_textures, float* normal_sums, int batch, int num_vertices, int num_faces,
+                                  const gendr_light_params* light, void* stream);
+int gendr_vertex_lighting_backward(const float* vertices, const int* face_index, int index_shared, const float* textures,
+                                   const float* normal_sums, const float* grad_lit_textures, float* grad_textures,
+                                   float* grad_vertices, float* grad_sums_scratch, int batch, int num_vertices, int num_faces,
+                                   const gendr_light_params* light, void* stream);
+
 /* The whole scene step in one call: world-space mesh -> Lighting -> LookAt/Look -> GenDR (the order every script of the
  * reference uses: experiments/opt_shape.py:257-259, train_reconstruction.py:228-230), surface textures.
  * Forward: camera kernel, lighting kernel, indexed face preprocessing, render kernel (4 launches; the reference issues ~40).
