@@ -25,10 +25,56 @@ static const render_launch_fn kLaunchTable[D_COUNT] = {
     launch_render_dist_10, launch_render_dist_11, launch_render_dist_12, launch_render_dist_13, launch_render_dist_14,
     launch_render_dist_15, launch_render_dist_16, launch_render_dist_17};
 
+// ---- longest-first CTA schedule (cta_to_tile, render_kernels.cuh) -----------------------------------------------------------------
+// count_tiles: the face adds 1 to every tile its candidate rectangle overlaps -- the tile's cost estimate.  Faces that reach more
+// than 128 tiles (dense regimes: the rectangle is the screen) are a uniform load and are left out (no 10^8 atomics in C4).
+__device__ __forceinline__ void count_tiles(const RenderParams& P, unsigned* __restrict__ counts, long long b, uint32_t wA, uint32_t wB) {
+    const int ix0 = (int)(wA & PIX_MASK), ix1 = (int)((wA >> 16) & PIX_MASK), iy0 = (int)(wB & PIX_MASK), iy1 = (int)((wB >> 16) & PIX_MASK);
+    if (ix1 < ix0 || iy1 < iy0) return;
+    const int tx0 = ix0 / TILE_W, tx1 = min(ix1 / TILE_W, P.tiles_x - 1), ty0 = iy0 / TILE_H, ty1 = min(iy1 / TILE_H, P.tiles_y - 1);
+    if (tx1 < tx0 || ty1 < ty0 || (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 128) return;
+    unsigned* c = counts + b * (long long)(P.tiles_x * P.tiles_y);
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(c + ty * P.tiles_x + tx, 1u);
+}
+// tile_order_kernel: counting sort of the n = B * tiles (item, tile) pairs by descending count, one CTA (n <= 2^18: a few
+// microseconds).  2048 bins: exact below 1024 faces, 8 faces per bin above; ties in arbitrary order.
+__device__ __forceinline__ unsigned tile_bin(unsigned c) {
+    const unsigned k = c < 1024u ? c : 1024u + min((c - 1024u) >> 3, 1023u);
+    return 2047u - k;
+}
+__global__ void __launch_bounds__(1024) tile_order_kernel(const unsigned* __restrict__ counts, unsigned* __restrict__ order, int n) {
+    __shared__ unsigned hist[2048];
+    __shared__ unsigned warp_sum[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    hist[tid] = 0u; hist[tid + 1024] = 0u;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) atomicAdd(&hist[tile_bin(counts[i])], 1u);
+    __syncthreads();
+    const unsigned h0 = hist[2 * tid], h1 = hist[2 * tid + 1], mine = h0 + h1;      // thread t owns bins 2t, 2t + 1
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) warp_sum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned w = warp_sum[tid];
+        unsigned x = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned u = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += u; }
+        warp_sum[tid] = x - w;
+    }
+    __syncthreads();
+    const unsigned excl = warp_sum[tid >> 5] + incl - mine;
+    hist[2 * tid] = excl; hist[2 * tid + 1] = excl + h0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) order[atomicAdd(&hist[tile_bin(counts[i])], 1u)] = (unsigned)i;
+}
+
 // ---- preprocessing kernel: one thread per (batch, face) -------------------------------------------------------
 __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ RenderParams P, const float* __restrict__ faces,
                                                    float* __restrict__ records, uint2* __restrict__ rects,
-                                                   float* __restrict__ faces_info) {
+                                                   float* __restrict__ faces_info, unsigned* __restrict__ tile_counts) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)P.B * P.F) return;
     float v[9];
@@ -40,12 +86,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const __grid_constant__ Rende
 #pragma unroll
     for (int k = 0; k < REC_WORDS / 4; ++k) dst[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
     rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+    if (tile_counts) count_tiles(P, tile_counts, i / P.F, __float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
 }
 
 // indexed variant: gathers the face's three vertices from vertices[B,V,3] through face_index (fused vertices[faces])
 __global__ void __launch_bounds__(256) prep_indexed_kernel(const __grid_constant__ RenderParams P, const float* __restrict__ vertices,
                                                            const int* __restrict__ face_index, long long index_batch_stride, int V,
-                                                           float* __restrict__ records, uint2* __restrict__ rects) {
+                                                           float* __restrict__ records, uint2* __restrict__ rects,
+                                                           unsigned* __restrict__ tile_counts) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)P.B * P.F) return;
     const long long b = i / P.F, f = i - b * P.F;
@@ -63,6 +111,7 @@ __global__ void __launch_bounds__(256) prep_indexed_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < REC_WORDS / 4; ++k) dst[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
     rects[i] = make_uint2(__float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
+    if (tile_counts) count_tiles(P, tile_counts, b, __float_as_uint(rec[R_PACK]), __float_as_uint(rec[R_PACK + 1]));
 }
 
 // zero-fill of the two gradient buffers of a backward call in ONE launch (two cudaMemsetAsync cost two launches; tiny scenes are
@@ -147,6 +196,8 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
     P.zrange = P.far_ - P.near_;                         // fp32 subtraction, as the kernels' gd_sub(far, near) was
     P.y_tau = 1.0f / P.dist_scale; P.y_gamma = 1.0f / P.rgb_gamma; P.y_zrange = 1.0f / P.zrange;      // IEEE: correctly rounded
+    P.cta_group = 16;
+    if (const char* ev = getenv("GENDR_B200_CTA_GROUP")) P.cta_group = std::max(1, atoi(ev));      // tuning experiments
     P.consts_ok = (rcp_in_range(P.dist_scale) && rcp_in_range(P.rgb_gamma) && rcp_in_range(P.zrange) && fabsf(P.near_) < 1e30f && fabsf(P.far_) < 1e30f) ? 1 : 0;
     P.tiles_x = (P.S + TILE_W - 1) / TILE_W; P.tiles_y = (P.S + TILE_H - 1) / TILE_H;
     return 0;
@@ -194,6 +245,34 @@ static uint2* ws_rects(void* ws, int B, int F) {
     return reinterpret_cast<uint2*>(reinterpret_cast<char*>(ws) + rec_bytes);
 }
 
+// longest-first schedule: [counts B*tiles | order B*tiles] (uint32) behind the rectangles; 32 KB per batch item hold up to 4096
+// tiles per image (image_size <= 1024).  Used when the grid is at least two waves of the machine -- below that every CTA is
+// resident from the start and the order is irrelevant.
+static const size_t kLptBytesPerItem = 32768;
+static bool lpt_enabled(const RenderParams& P) {
+    const long long tiles = (long long)P.tiles_x * P.tiles_y, n = tiles * P.B;
+    return n >= 2 * 148 * 4 && tiles * 8 <= (long long)kLptBytesPerItem && n <= (1ll << 18);
+}
+static unsigned* ws_tile_counts(void* ws, int B, int F) {
+    size_t rct_bytes = ((size_t)B * F * sizeof(uint2) + 255) & ~(size_t)255;
+    return reinterpret_cast<unsigned*>(reinterpret_cast<char*>(ws_rects(ws, B, F)) + rct_bytes + 256);
+}
+static unsigned* ws_cta_order(void* ws, const RenderParams& P) { return ws_tile_counts(ws, P.B, P.F) + (size_t)P.B * P.tiles_x * P.tiles_y; }
+static int lpt_begin(const RenderParams& P, void* ws, cudaStream_t st, unsigned** counts) {
+    *counts = nullptr;
+    if (!lpt_enabled(P)) return 0;
+    *counts = ws_tile_counts(ws, P.B, P.F);
+    GENDR_CUDA(cudaMemsetAsync(*counts, 0, (size_t)P.B * P.tiles_x * P.tiles_y * sizeof(unsigned), st), "clearing the tile counters");
+    return 0;
+}
+static int lpt_finish(const RenderParams& P, void* ws, cudaStream_t st) {
+    if (!lpt_enabled(P)) return 0;
+    tile_order_kernel<<<1, 1024, 0, st>>>(ws_tile_counts(ws, P.B, P.F), ws_cta_order(ws, P), P.B * P.tiles_x * P.tiles_y);
+    g_launches++;
+    GENDR_CUDA(cudaGetLastError(), "tile_order_kernel launch");
+    return 0;
+}
+
 static int zero_grads2(float* a, long long n_a, float* b, long long n_b, cudaStream_t st) {
     if (!a) n_a = 0;
     if (!b) n_b = 0;
@@ -215,10 +294,12 @@ static int zero_grads2(float* a, long long n_a, float* b, long long n_b, cudaStr
 static int run_prep(const RenderParams& P, const float* faces, float* faces_info, void* ws, cudaStream_t st) {
     const long long n = (long long)P.B * P.F;
     if (n == 0) return 0;
-    prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, faces, ws_records(ws), ws_rects(ws, P.B, P.F), faces_info);
+    unsigned* counts;
+    if (int e = lpt_begin(P, ws, st, &counts)) return e;
+    prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, faces, ws_records(ws), ws_rects(ws, P.B, P.F), faces_info, counts);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "prep_kernel launch");
-    return 0;
+    return lpt_finish(P, ws, st);
 }
 
 static int run_render(const RenderParams& P, const KernelIO& io, bool backward, cudaStream_t st) {
@@ -244,7 +325,9 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
     cfg.fast = (P.aggr_rgb_func == 1 && P.texture_type == 0 && P.T == 1 && !P.dist_squared &&
                 (P.aggr_alpha_func == T_PROBABILISTIC || P.aggr_alpha_func == T_EINSTEIN || yager2));
     cfg.tcn_mode = cfg.fast ? (yager2 ? 4 : P.aggr_alpha_func) : (P.aggr_alpha_func >= T_HAMACHER ? 1 : 0);
-    cudaError_t e = kLaunchTable[P.dist_func](P, io, cfg);
+    KernelIO io2 = io;      // (records = start of the workspace)
+    io2.cta_order = (lpt_enabled(P) && cfg.grid.y == 1) ? ws_cta_order(const_cast<float*>(io.records), P) : nullptr;
+    cudaError_t e = kLaunchTable[P.dist_func](P, io2, cfg);
     g_launches++;
     if (e != cudaSuccess) return fail((int)e, backward ? "backward render_kernel launch" : "forward render_kernel launch");
     return 0;
@@ -354,7 +437,7 @@ struct HostPathScratch {      // one per device (process-wide): a process may dr
     cudaStream_t stream = nullptr;                 // compute
     cudaStream_t h2d = nullptr, d2h = nullptr;     // copy engines, overlapped with the kernels
     static const int MAX_CHUNKS = 8;
-    cudaEvent_t in_ready[MAX_CHUNKS] = {}, done[MAX_CHUNKS] = {};
+    cudaEvent_t in_ready[2 * MAX_CHUNKS] = {}, done[2 * MAX_CHUNKS] = {};      // [chunk] forward inputs / outputs, [MAX_CHUNKS + chunk] backward
 };
 static const int kMaxDevices = 64;
 static HostPathScratch g_scratch_of[kMaxDevices];
@@ -373,7 +456,7 @@ size_t gendr_workspace_bytes(int batch, int faces) {
     if (batch < 0 || faces < 0) return 0;
     size_t rec = ((size_t)batch * faces * REC_BYTES + 255) & ~(size_t)255;
     size_t rct = ((size_t)batch * faces * sizeof(uint2) + 255) & ~(size_t)255;
-    return rec + rct + 256;
+    return rec + rct + 256 + (size_t)batch * kLptBytesPerItem;      // records | rectangles | slack | tile counters + CTA order
 }
 
 static int gendr_forward_render_chunk(const float* faces, const float* textures, long long tex_elems, float* aggrs_info, float* soft_colors,
@@ -484,10 +567,16 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     const size_t e_faces = (size_t)num_faces * 9, e_tex = (size_t)num_faces * texture_size * 3, e_col = 4 * S * S, e_agg = 2 * S * S;
     const size_t n_faces = (size_t)batch * e_faces * 4, n_tex = (size_t)batch * e_tex * 4;
     const size_t n_col = (size_t)batch * e_col * 4, n_agg = (size_t)batch * e_agg * 4;
-    const size_t n_ws = gendr_workspace_bytes(batch, num_faces);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const bool bwd = h_grad_soft_colors && h_grad_faces;
-    const size_t need = al(n_faces) * 2 + al(n_tex) * 2 + al(n_col) * 2 + al(n_agg) + al(n_ws);
+    // The batch is cut into up to four slices that move through upload -> forward -> backward -> download as a pipeline: only the
+    // first slice's geometry upload and the last slice's gradient download are exposed (one slice: ~0.5 ms each for C3, of a
+    // 9 ms step).  Slices keep >= 8 items so that every kernel still fills the machine several times over.
+    int n_chunks = std::max(1, std::min(4, batch / 8));
+    if (const char* ev = getenv("GENDR_B200_HOST_CHUNKS")) n_chunks = std::max(1, std::min(std::min(HostPathScratch::MAX_CHUNKS, batch), atoi(ev)));
+    const int per = (batch + n_chunks - 1) / n_chunks;
+    const size_t ws_chunk = al(gendr_workspace_bytes(per, num_faces));
+    const size_t need = al(n_faces) * 2 + al(n_tex) * 2 + al(n_col) * 2 + al(n_agg) + ws_chunk * n_chunks;
     int dev = 0;
     GENDR_CUDA(cudaGetDevice(&dev), "cudaGetDevice");
     if (dev < 0 || dev >= kMaxDevices) return fail(GENDR_ERR_INVALID_ARGUMENT, "device ordinal out of range for the host-buffer path");
@@ -497,7 +586,7 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.h2d, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.d2h, cudaStreamNonBlocking), "cudaStreamCreate");
-        for (int i = 0; i < HostPathScratch::MAX_CHUNKS; ++i) {
+        for (int i = 0; i < 2 * HostPathScratch::MAX_CHUNKS; ++i) {
             GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.in_ready[i], cudaEventDisableTiming), "cudaEventCreate");
             GENDR_CUDA(cudaEventCreateWithFlags(&g_scratch.done[i], cudaEventDisableTiming), "cudaEventCreate");
         }
@@ -516,32 +605,51 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     float* d_col = (float*)p; p += al(n_col);
     float* d_gcol = (float*)p; p += al(n_col);
     float* d_agg = (float*)p; p += al(n_agg);
-    void* d_ws = p;
-    // Three streams: uploads / compute / downloads.  The cotangent upload (the largest input) overlaps the forward
-    // kernel, the image download overlaps the backward kernel; kernels always see the full batch (full-size grids).
+    char* d_ws = p;
+    const int NC = HostPathScratch::MAX_CHUNKS;
+    // Three streams: uploads / compute / downloads.  Uploads in the order the kernels need them: all textures (the forward kernel
+    // reads one texel past its slice, quirk Q3), the slices' geometry, then the slices' cotangents (the largest input; overlaps
+    // the forward kernels).  Image downloads overlap the remaining kernels.
     GENDR_CUDA(cudaMemcpyAsync(d_tex, h_textures, n_tex, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D textures");
-    GENDR_CUDA(cudaMemcpyAsync(d_faces, h_faces, n_faces, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D faces");
-    GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[0], g_scratch.h2d), "event record");
-    if (bwd) {
-        GENDR_CUDA(cudaMemcpyAsync(d_gcol, h_grad_soft_colors, n_col, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D grad_soft_colors");
-        GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[1], g_scratch.h2d), "event record");
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = c * per, nb = std::min(per, batch - b0);
+        if (nb <= 0) break;
+        GENDR_CUDA(cudaMemcpyAsync(d_faces + (size_t)b0 * e_faces, h_faces + (size_t)b0 * e_faces, (size_t)nb * e_faces * 4, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D faces");
+        GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[c], g_scratch.h2d), "event record");
     }
-    GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[0], 0), "stream wait");
-    if (int e = gendr_forward_render_chunk(d_faces, d_tex, (long long)batch * (long long)e_tex, d_agg, d_col, batch, num_faces, texture_size,
-                                           params, d_ws, n_ws, g_scratch.stream)) return e;
-    GENDR_CUDA(cudaEventRecord(g_scratch.done[0], g_scratch.stream), "event record");
-    GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[0], 0), "stream wait");
-    GENDR_CUDA(cudaMemcpyAsync(h_soft_colors, d_col, n_col, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H soft_colors");
-    if (bwd) {
-        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[1], 0), "stream wait");
-        if (int e = gendr_backward_render_chunk(d_faces, d_tex, (long long)batch * (long long)e_tex, d_col, d_agg, d_gfaces,
-                                                h_grad_textures ? d_gtex : nullptr, d_gcol, batch, num_faces, texture_size, params, d_ws, n_ws,
-                                                g_scratch.stream)) return e;
-        GENDR_CUDA(cudaEventRecord(g_scratch.done[1], g_scratch.stream), "event record");
-        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[1], 0), "stream wait");
-        GENDR_CUDA(cudaMemcpyAsync(h_grad_faces, d_gfaces, n_faces, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_faces");
-        if (h_grad_textures) GENDR_CUDA(cudaMemcpyAsync(h_grad_textures, d_gtex, n_tex, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_textures");
+    if (bwd)
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b0 = c * per, nb = std::min(per, batch - b0);
+            if (nb <= 0) break;
+            GENDR_CUDA(cudaMemcpyAsync(d_gcol + (size_t)b0 * e_col, h_grad_soft_colors + (size_t)b0 * e_col, (size_t)nb * e_col * 4, cudaMemcpyHostToDevice, g_scratch.h2d), "H2D grad_soft_colors");
+            GENDR_CUDA(cudaEventRecord(g_scratch.in_ready[NC + c], g_scratch.h2d), "event record");
+        }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b0 = c * per, nb = std::min(per, batch - b0);
+        if (nb <= 0) break;
+        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[c], 0), "stream wait");
+        if (int e = gendr_forward_render_chunk(d_faces + (size_t)b0 * e_faces, d_tex + (size_t)b0 * e_tex, (long long)(batch - b0) * (long long)e_tex,
+                                               d_agg + (size_t)b0 * e_agg, d_col + (size_t)b0 * e_col, nb, num_faces, texture_size, params,
+                                               d_ws + (size_t)c * ws_chunk, ws_chunk, g_scratch.stream)) return e;
+        GENDR_CUDA(cudaEventRecord(g_scratch.done[c], g_scratch.stream), "event record");
+        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[c], 0), "stream wait");
+        GENDR_CUDA(cudaMemcpyAsync(h_soft_colors + (size_t)b0 * e_col, d_col + (size_t)b0 * e_col, (size_t)nb * e_col * 4, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H soft_colors");
     }
+    if (bwd)
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b0 = c * per, nb = std::min(per, batch - b0);
+            if (nb <= 0) break;
+            GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[NC + c], 0), "stream wait");
+            if (int e = gendr_backward_render_chunk(d_faces + (size_t)b0 * e_faces, d_tex + (size_t)b0 * e_tex, (long long)(batch - b0) * (long long)e_tex,
+                                                    d_col + (size_t)b0 * e_col, d_agg + (size_t)b0 * e_agg, d_gfaces + (size_t)b0 * e_faces,
+                                                    h_grad_textures ? d_gtex + (size_t)b0 * e_tex : nullptr, d_gcol + (size_t)b0 * e_col, nb, num_faces,
+                                                    texture_size, params, d_ws + (size_t)c * ws_chunk, ws_chunk, g_scratch.stream)) return e;
+            GENDR_CUDA(cudaEventRecord(g_scratch.done[NC + c], g_scratch.stream), "event record");
+            GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[NC + c], 0), "stream wait");
+            GENDR_CUDA(cudaMemcpyAsync(h_grad_faces + (size_t)b0 * e_faces, d_gfaces + (size_t)b0 * e_faces, (size_t)nb * e_faces * 4, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_faces");
+            if (h_grad_textures)
+                GENDR_CUDA(cudaMemcpyAsync(h_grad_textures + (size_t)b0 * e_tex, d_gtex + (size_t)b0 * e_tex, (size_t)nb * e_tex * 4, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_textures");
+        }
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.d2h), "host-path stream synchronize");
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.stream), "host-path stream synchronize");
     return 0;
@@ -558,7 +666,7 @@ void gendr_release_host_scratch(void) {
         if (sc.ready) {
             cudaStreamSynchronize(sc.stream); cudaStreamSynchronize(sc.h2d); cudaStreamSynchronize(sc.d2h);
             cudaStreamDestroy(sc.stream); cudaStreamDestroy(sc.h2d); cudaStreamDestroy(sc.d2h);
-            for (int i = 0; i < HostPathScratch::MAX_CHUNKS; ++i) { cudaEventDestroy(sc.in_ready[i]); cudaEventDestroy(sc.done[i]); }
+            for (int i = 0; i < 2 * HostPathScratch::MAX_CHUNKS; ++i) { cudaEventDestroy(sc.in_ready[i]); cudaEventDestroy(sc.done[i]); }
             sc.stream = sc.h2d = sc.d2h = nullptr;
             sc.ready = false;
         }
@@ -576,10 +684,13 @@ static int forward_indexed_impl(const RenderParams& P, const float* vertices, co
                                 float* aggrs_info, float* soft_colors, float* pooled_colors, int num_vertices, void* workspace, cudaStream_t st) {
     const long long n = (long long)P.B * P.F;
     if (n > 0) {
+        unsigned* counts;
+        if (int e = lpt_begin(P, workspace, st, &counts)) return e;
         prep_indexed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, vertices, face_index, index_shared ? 0 : (long long)P.F * 3, num_vertices,
-                                                                       ws_records(workspace), ws_rects(workspace, P.B, P.F));
+                                                                       ws_records(workspace), ws_rects(workspace, P.B, P.F), counts);
         g_launches++;
         GENDR_CUDA(cudaGetLastError(), "prep_indexed_kernel launch");
+        if (int e = lpt_finish(P, workspace, st)) return e;
     }
     KernelIO io;
     memset(&io, 0, sizeof io);
