@@ -434,7 +434,8 @@ struct HostPathScratch {      // one per device (process-wide): a process may dr
     bool ready = false;
     size_t cap = 0;
     char* base = nullptr;
-    cudaStream_t stream = nullptr;                 // compute
+    cudaStream_t stream = nullptr;                 // compute, slice 0
+    cudaStream_t extra[3] = {};                    // compute, slices 1..3: a slice's kernels fill the drain of the previous slice's
     cudaStream_t h2d = nullptr, d2h = nullptr;     // copy engines, overlapped with the kernels
     static const int MAX_CHUNKS = 8;
     cudaEvent_t in_ready[2 * MAX_CHUNKS] = {}, done[2 * MAX_CHUNKS] = {};      // [chunk] forward inputs / outputs, [MAX_CHUNKS + chunk] backward
@@ -573,7 +574,7 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     // first slice's geometry upload and the last slice's gradient download are exposed (one slice: ~0.5 ms each for C3, of a
     // 9 ms step).  Slices keep >= 8 items so that every kernel still fills the machine several times over.
     int n_chunks = std::max(1, std::min(4, batch / 8));
-    if (const char* ev = getenv("GENDR_B200_HOST_CHUNKS")) n_chunks = std::max(1, std::min(std::min(HostPathScratch::MAX_CHUNKS, batch), atoi(ev)));
+    if (const char* ev = getenv("GENDR_B200_HOST_CHUNKS")) n_chunks = std::max(1, std::min(std::min(4, batch), atoi(ev)));      // tuning experiments
     const int per = (batch + n_chunks - 1) / n_chunks;
     const size_t ws_chunk = al(gendr_workspace_bytes(per, num_faces));
     const size_t need = al(n_faces) * 2 + al(n_tex) * 2 + al(n_col) * 2 + al(n_agg) + ws_chunk * n_chunks;
@@ -584,6 +585,7 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     std::lock_guard<std::mutex> lock(g_scratch.mu);
     if (!g_scratch.ready) {
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int i = 0; i < 3; ++i) GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.extra[i], cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.h2d, cudaStreamNonBlocking), "cudaStreamCreate");
         GENDR_CUDA(cudaStreamCreateWithFlags(&g_scratch.d2h, cudaStreamNonBlocking), "cudaStreamCreate");
         for (int i = 0; i < 2 * HostPathScratch::MAX_CHUNKS; ++i) {
@@ -607,6 +609,8 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     float* d_agg = (float*)p; p += al(n_agg);
     char* d_ws = p;
     const int NC = HostPathScratch::MAX_CHUNKS;
+    // one compute stream per slice: the slices' kernels are independent, so slice c + 1 fills the SMs that slice c's last CTAs leave idle
+    auto cs = [&](int c) { return c == 0 ? g_scratch.stream : g_scratch.extra[c - 1]; };
     // Three streams: uploads / compute / downloads.  Uploads in the order the kernels need them: all textures (the forward kernel
     // reads one texel past its slice, quirk Q3), the slices' geometry, then the slices' cotangents (the largest input; overlaps
     // the forward kernels).  Image downloads overlap the remaining kernels.
@@ -627,11 +631,11 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
     for (int c = 0; c < n_chunks; ++c) {
         const int b0 = c * per, nb = std::min(per, batch - b0);
         if (nb <= 0) break;
-        GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[c], 0), "stream wait");
+        GENDR_CUDA(cudaStreamWaitEvent(cs(c), g_scratch.in_ready[c], 0), "stream wait");
         if (int e = gendr_forward_render_chunk(d_faces + (size_t)b0 * e_faces, d_tex + (size_t)b0 * e_tex, (long long)(batch - b0) * (long long)e_tex,
                                                d_agg + (size_t)b0 * e_agg, d_col + (size_t)b0 * e_col, nb, num_faces, texture_size, params,
-                                               d_ws + (size_t)c * ws_chunk, ws_chunk, g_scratch.stream)) return e;
-        GENDR_CUDA(cudaEventRecord(g_scratch.done[c], g_scratch.stream), "event record");
+                                               d_ws + (size_t)c * ws_chunk, ws_chunk, cs(c))) return e;
+        GENDR_CUDA(cudaEventRecord(g_scratch.done[c], cs(c)), "event record");
         GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[c], 0), "stream wait");
         GENDR_CUDA(cudaMemcpyAsync(h_soft_colors + (size_t)b0 * e_col, d_col + (size_t)b0 * e_col, (size_t)nb * e_col * 4, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H soft_colors");
     }
@@ -639,12 +643,12 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
         for (int c = 0; c < n_chunks; ++c) {
             const int b0 = c * per, nb = std::min(per, batch - b0);
             if (nb <= 0) break;
-            GENDR_CUDA(cudaStreamWaitEvent(g_scratch.stream, g_scratch.in_ready[NC + c], 0), "stream wait");
+            GENDR_CUDA(cudaStreamWaitEvent(cs(c), g_scratch.in_ready[NC + c], 0), "stream wait");
             if (int e = gendr_backward_render_chunk(d_faces + (size_t)b0 * e_faces, d_tex + (size_t)b0 * e_tex, (long long)(batch - b0) * (long long)e_tex,
                                                     d_col + (size_t)b0 * e_col, d_agg + (size_t)b0 * e_agg, d_gfaces + (size_t)b0 * e_faces,
                                                     h_grad_textures ? d_gtex + (size_t)b0 * e_tex : nullptr, d_gcol + (size_t)b0 * e_col, nb, num_faces,
-                                                    texture_size, params, d_ws + (size_t)c * ws_chunk, ws_chunk, g_scratch.stream)) return e;
-            GENDR_CUDA(cudaEventRecord(g_scratch.done[NC + c], g_scratch.stream), "event record");
+                                                    texture_size, params, d_ws + (size_t)c * ws_chunk, ws_chunk, cs(c))) return e;
+            GENDR_CUDA(cudaEventRecord(g_scratch.done[NC + c], cs(c)), "event record");
             GENDR_CUDA(cudaStreamWaitEvent(g_scratch.d2h, g_scratch.done[NC + c], 0), "stream wait");
             GENDR_CUDA(cudaMemcpyAsync(h_grad_faces + (size_t)b0 * e_faces, d_gfaces + (size_t)b0 * e_faces, (size_t)nb * e_faces * 4, cudaMemcpyDeviceToHost, g_scratch.d2h), "D2H grad_faces");
             if (h_grad_textures)
@@ -652,6 +656,7 @@ int gendr_render_forward_backward_host(const float* h_faces, const float* h_text
         }
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.d2h), "host-path stream synchronize");
     GENDR_CUDA(cudaStreamSynchronize(g_scratch.stream), "host-path stream synchronize");
+    for (int i = 0; i < 3; ++i) GENDR_CUDA(cudaStreamSynchronize(g_scratch.extra[i]), "host-path stream synchronize");
     return 0;
 }
 
@@ -666,6 +671,7 @@ void gendr_release_host_scratch(void) {
         if (sc.ready) {
             cudaStreamSynchronize(sc.stream); cudaStreamSynchronize(sc.h2d); cudaStreamSynchronize(sc.d2h);
             cudaStreamDestroy(sc.stream); cudaStreamDestroy(sc.h2d); cudaStreamDestroy(sc.d2h);
+            for (int i = 0; i < 3; ++i) { cudaStreamSynchronize(sc.extra[i]); cudaStreamDestroy(sc.extra[i]); sc.extra[i] = nullptr; }
             for (int i = 0; i < 2 * HostPathScratch::MAX_CHUNKS; ++i) { cudaEventDestroy(sc.in_ready[i]); cudaEventDestroy(sc.done[i]); }
             sc.stream = sc.h2d = sc.d2h = nullptr;
             sc.ready = false;
