@@ -305,9 +305,9 @@ static int zero_grads2(float* a, long long n_a, float* b, long long n_b, cudaStr
 
 static int run_prep(const RenderParams& P, const float* faces, float* faces_info, void* ws, cudaStream_t st) {
     const long long n = (long long)P.B * P.F;
-    if (n == 0) return 0;
     unsigned* counts;
     if (int e = lpt_begin(P, ws, st, &counts)) return e;
+    if (n == 0) return lpt_finish(P, ws, st);      // no faces: the render kernel still needs a valid CTA order
     prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, faces, ws_records(ws), ws_rects(ws, P.B, P.F), faces_info, counts);
     g_launches++;
     GENDR_CUDA(cudaGetLastError(), "prep_kernel launch");
@@ -532,7 +532,7 @@ static int backward_render_impl(const char* who, bool batchsum, const float* fac
                                 void* workspace, size_t workspace_bytes, void* stream) {
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, who);
-    if (batch == 0) return 0;
+    if (batch == 0 || num_faces == 0) return 0;      // no faces: every gradient buffer is empty
     if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_soft_colors || !workspace) return fail(GENDR_ERR_INVALID_ARGUMENT, who);
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
     DeviceScope dev;
@@ -701,9 +701,10 @@ static int check_aa(const RenderParams& P, const void* pooled_or_flag) {
 static int forward_indexed_impl(const RenderParams& P, const float* vertices, const int* face_index, int index_shared, const float* textures,
                                 float* aggrs_info, float* soft_colors, float* pooled_colors, int num_vertices, void* workspace, cudaStream_t st) {
     const long long n = (long long)P.B * P.F;
+    unsigned* counts;
+    if (int e = lpt_begin(P, workspace, st, &counts)) return e;
+    if (n == 0) { if (int e = lpt_finish(P, workspace, st)) return e; }
     if (n > 0) {
-        unsigned* counts;
-        if (int e = lpt_begin(P, workspace, st, &counts)) return e;
         prep_indexed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, vertices, face_index, index_shared ? 0 : (long long)P.F * 3, num_vertices,
                                                                        ws_records(workspace), ws_rects(workspace, P.B, P.F), counts);
         g_launches++;
@@ -758,6 +759,11 @@ int gendr_backward_render_indexed(const int* face_index, int index_shared, const
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_indexed");
     if (batch == 0) return 0;
+    if (num_faces == 0) {      // no faces: the vertex gradient is zero
+        if (!grad_vertices || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed");
+        if (zero_grads) GENDR_CUDA(cudaMemsetAsync(grad_vertices, 0, (size_t)batch * num_vertices * 3 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)), "zero gradient buffer");
+        return 0;
+    }
     if (!face_index || !textures || !soft_colors || !aggrs_info || !grad_vertices || !grad_soft_colors || !workspace || num_vertices < 1)
         return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
@@ -775,6 +781,11 @@ int gendr_backward_render_indexed_batchsum(const int* face_index, int index_shar
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_indexed_batchsum");
     if (batch == 0) return 0;
+    if (num_faces == 0) {      // no faces: the vertex gradient is zero
+        if (!grad_vertices_sum || num_vertices < 1) return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed_batchsum");
+        if (zero_grads) GENDR_CUDA(cudaMemsetAsync(grad_vertices_sum, 0, (size_t)1 * num_vertices * 3 * sizeof(float), reinterpret_cast<cudaStream_t>(stream)), "zero gradient buffer");
+        return 0;
+    }
     if (!face_index || !textures || !soft_colors || !aggrs_info || !grad_vertices_sum || !grad_soft_colors || !workspace || num_vertices < 1)
         return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_indexed_batchsum");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
@@ -814,7 +825,7 @@ int gendr_backward_render_aa(const float* faces, const float* textures, const fl
                              void* stream) {
     RenderParams P;
     if (int e = make_params(P, batch, num_faces, texture_size, params)) return fail(e, "invalid argument to gendr_backward_render_aa");
-    if (batch == 0) return 0;
+    if (batch == 0 || num_faces == 0) return 0;
     if (!faces || !textures || !soft_colors || !aggrs_info || !grad_faces || !grad_pooled_colors || !workspace)
         return fail(GENDR_ERR_INVALID_ARGUMENT, "null pointer passed to gendr_backward_render_aa");
     if (workspace_bytes < gendr_workspace_bytes(batch, num_faces)) return fail(GENDR_ERR_WORKSPACE_TOO_SMALL, "workspace too small (see gendr_workspace_bytes)");
