@@ -29,3 +29,14 @@ img = gd.functional.render_scene(v, faces.to(dev), tex, eyes, camera=dict(viewin
                                  dist_scale=0.03, anti_aliasing=True)
 img.backward(torch.ones_like(img)); torch.cuda.synchronize()
 print('scene', float(img.sum()), float(v.grad.abs().sum()), float(eyes.grad.abs().sum()))
+# a grid of >= 2 waves of CTAs (5 x 256 tiles): tile counters, the counting sort and the sorted CTA schedule; vertex-texture lighting
+fv, ft = scenes.soup(60, batch=5, seed=7, size=0.3)
+a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
+img = gd.functional.render(a, b, image_size=256, dist_func='gaussian', aggr_alpha_func='einstein', dist_scale=0.01, dist_eps=30.)
+img.backward(torch.ones_like(img)); torch.cuda.synchronize()
+print('sorted schedule', float(img.sum()), float(a.grad.abs().sum()))
+vt = torch.rand(3, verts.shape[0], 3).to(dev).requires_grad_(True)
+vv = (verts * 0.5)[None].repeat(3, 1, 1).to(dev).requires_grad_(True)
+lit = gd.functional.vertex_lighting(vv, faces.to(dev), vt, direction=(0.3, 0.8, -0.5))
+lit.backward(torch.ones_like(lit)); torch.cuda.synchronize()
+print('vertex lighting', float(lit.sum()), float(vv.grad.abs().sum()))
