@@ -55,7 +55,8 @@ typedef struct gendr_render_params {
     float background[3];
 } gendr_render_params;
 
-/* Scratch the library needs between forward and backward: per-face records (176 B) + packed pixel rects (8 B). */
+/* Scratch the library needs between forward and backward: per-face records (176 B) + packed pixel rects (8 B), and per batch
+ * item 32 KB for the tile counters and the longest-first CTA order of large grids (up to 4096 tiles per image). */
 size_t gendr_workspace_bytes(int batch, int faces);
 
 /* Forward.  background_prefilled != 0: read the background from soft_colors' RGB planes exactly as the reference
