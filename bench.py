@@ -426,6 +426,9 @@ def main():
         raise SystemExit('bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm')
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    # one process per GPU: keep this rank (and the pinned host buffers of the e2e leg) on the CPUs local to its GPU
+    from gendr_b200.parallel import bind_host_to_device
+    host_cpus = bind_host_to_device(local_rank) if (world > 1 and not os.environ.get('GENDR_B200_NO_AFFINITY')) else None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     lib = _lib.load()
@@ -496,7 +499,7 @@ def main():
     equal, c4 = None, None
     if world > 1:
         equal = sharded_equals_single(rig, rank, world, dev)
-        if args.workload != 'c4':
+        if args.workload != 'c4' and not os.environ.get('GENDR_B200_BENCH_SKIP_C4'):      # (the skip is for tuning runs only)
             del rig
             torch.cuda.empty_cache()
             rig4 = Rig('c4', 0, rank, world, dev)
@@ -567,6 +570,9 @@ def main():
             'value_public_api': {'value': pairs_per_step / (api_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': api_ms},
             'kernel_ms': {'forward': res['fwd_ms'], 'backward': bwd_ms, 'allreduce': res['allreduce_ms']},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline}
+    if world > 1:
+        line['notes']['host_affinity'] = ('rank 0 bound to the %d CPUs local to its GPU (gendr_b200.parallel.bind_host_to_device); every rank does the same'
+                                          % len(host_cpus)) if host_cpus else 'unchanged (no NUMA-local CPU list found, or it is the whole allowed set)'
     if equal is not None:
         line['sharded_equals_single'] = bool(equal['ok'])
         line['sharded_check'] = equal

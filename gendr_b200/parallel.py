@@ -7,8 +7,41 @@ exchange step exists only when the mesh is shared across the batch (vertices.rep
 a local sum over the rank's slice followed by ONE all-reduce(SUM) of [F,3,3] fp32 (295 KB at F = 8192) on the same
 stream, right behind the backward kernel.  The reference has no multi-GPU support at all.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device(device_index, sysfs='/sys/bus/pci/devices'):
+    """Restrict this process to the CPUs that are local to GPU `device_index` (its PCIe root's NUMA node, from sysfs), so that
+    the pinned host buffers it allocates afterwards are local to that GPU.  With one process per GPU and no affinity (torchrun
+    sets none) all ranks' pinned buffers may land on one socket and half of the host<->device copies cross the socket
+    interconnect: the end-to-end step of an 8-GPU job is then bound by that, not by the kernels.  Returns the CPU set applied,
+    or None when nothing was changed (no sysfs entry, no overlap with the allowed CPUs, non-Linux)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(os.path.join(sysfs, bdf, 'local_cpulist')) as fh:
+            local = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = local & allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None
 
 
 def shard_bounds(batch, rank, world_size):
