@@ -82,3 +82,30 @@ def test_sharded_render_equals_single_process(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(tmp_path / 'result.txt').read() == 'True True'
+
+
+def test_bind_host_to_device_helper(tmp_path, monkeypatch):
+    """NUMA-local binding of a rank: cpulist parsing, and a silent no-op when there is nothing to bind to (no GPU, no sysfs entry)."""
+    import os
+    from gendr_b200 import parallel
+    assert parallel._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert parallel._parse_cpulist('\n') == set()
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_host_to_device(0, sysfs=str(tmp_path)) is None      # no CUDA device here / no sysfs entry: unchanged
+    assert os.sched_getaffinity(0) == before
+
+    class _Props(object):
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0x1b, 0
+    monkeypatch.setattr(parallel.torch.cuda, 'get_device_properties', lambda i: _Props())
+    d = tmp_path / '0000:1b:00.0'
+    d.mkdir()
+    one = sorted(before)[0]
+    (d / 'local_cpulist').write_text('%d\n' % one)
+    try:
+        got = parallel.bind_host_to_device(0, sysfs=str(tmp_path))
+        if len(before) > 1:
+            assert got == {one} and os.sched_getaffinity(0) == {one}
+        else:
+            assert got is None
+    finally:
+        os.sched_setaffinity(0, before)
