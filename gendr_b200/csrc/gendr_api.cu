@@ -207,6 +207,7 @@ static int make_params(RenderParams& P, int B, int F, int T, const gendr_render_
     P.inv_tcn_p = (float)(1. / (double)u->aggr_alpha_t_conorm_p);
     P.zrange = P.far_ - P.near_;                         // fp32 subtraction, as the kernels' gd_sub(far, near) was
     P.y_tau = 1.0f / P.dist_scale; P.y_gamma = 1.0f / P.rgb_gamma; P.y_zrange = 1.0f / P.zrange;      // IEEE: correctly rounded
+    P.k_zs = (float)(1.4426950408889634 / (double)P.rgb_gamma); P.k_cz = (float)(1.0 / ((double)P.rgb_gamma * (double)P.zrange));
     P.cta_group = 16;
     if (const char* ev = getenv("GENDR_B200_CTA_GROUP")) P.cta_group = std::max(1, atoi(ev));      // tuning experiments
     P.consts_ok = (rcp_in_range(P.dist_scale) && rcp_in_range(P.rgb_gamma) && rcp_in_range(P.zrange) && fabsf(P.near_) < 1e30f && fabsf(P.far_) < 1e30f) ? 1 : 0;
