@@ -158,3 +158,58 @@ def test_batch_summed_backward_equals_sum_of_per_item_gradients():
                                                           g.data_ptr(), 0, 4, V, F, 1, C.byref(params), 1, ws.data_ptr(), ws.numel(), st))
     want = gv.double().sum(0)
     assert float((gvs.double() - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
+def test_sorted_cta_schedule_is_a_permutation_heaviest_first():
+    """Grids of >= 2 waves of CTAs run longest-first within groups of 16 batch items (tile_order_kernel): the list the render kernels
+    index with blockIdx.x must contain every (item, tile) exactly once, grouped by item group, with the candidate counts (exact below
+    128 faces, binned by 16 above) non-increasing inside a group; the counts must equal a host recount from the packed rectangles."""
+    dev = _dev()
+    lib = _lib.load()
+    B, S = 20, 256                                        # 20 x 256 tiles = 5120 CTAs; groups of 16 and 4 items
+    fv, ft = scenes.soup(300, batch=B, seed=9, size=0.25)
+    F, tiles = fv.shape[1], (S // 16) ** 2
+    params = ext.make_params(S, 4, 0.01, False, 0., 0., 30., 3, 0., 1, 1e-3, 1e-3, 1., 100., False, 0)
+    faces, tex = fv.to(dev).view(B, F, 9).contiguous(), ft.to(dev).contiguous()
+    colors, aggrs = torch.empty(B, 4, S, S, device=dev), torch.empty(B, 2, S, S, device=dev)
+    ws = torch.empty(lib.gendr_workspace_bytes(B, F), dtype=torch.uint8, device=dev)
+    _lib.check(lib.gendr_forward_render(faces.data_ptr(), tex.data_ptr(), None, aggrs.data_ptr(), colors.data_ptr(), B, F, 1, C.byref(params), 0,
+                                        ws.data_ptr(), ws.numel(), None))
+    torch.cuda.synchronize()
+    al = lambda x: (x + 255) & ~255
+    off = al(B * F * 176) + al(B * F * 8) + 256
+    n = B * tiles
+    counts = ws[off:off + 4 * n].view(torch.int32).cpu().numpy()
+    order = ws[off + 4 * n:off + 8 * n].view(torch.int32).cpu().numpy()
+    assert sorted(order.tolist()) == list(range(n))
+    group_of = (order // tiles) // 16
+    assert (np.diff(group_of) >= 0).all()                 # item groups in ascending order
+    key = np.where(counts < 128, counts, 128 + np.minimum((counts - 128) >> 4, 127))[order]
+    for g in np.unique(group_of):
+        k = key[group_of == g]
+        assert (np.diff(k) <= 0).all(), g                 # heaviest tiles of the group first
+    # host recount from the packed rectangles (word30 / word31 of the face records)
+    rec = ws[:B * F * 176].view(torch.int32).view(B, F, 44)[:, :, 30:32].cpu().numpy().astype(np.int64)
+    want = np.zeros((B, S // 16, S // 16), np.int64)
+    for b in range(B):
+        for f in range(F):
+            wa, wb = rec[b, f, 0] & 0xffffffff, rec[b, f, 1] & 0xffffffff
+            ix0, ix1, iy0, iy1 = wa & 0x3fff, (wa >> 16) & 0x3fff, wb & 0x3fff, (wb >> 16) & 0x3fff
+            if ix1 < ix0 or iy1 < iy0:
+                continue
+            tx0, tx1, ty0, ty1 = ix0 // 16, min(ix1 // 16, S // 16 - 1), iy0 // 16, min(iy1 // 16, S // 16 - 1)
+            if (tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 128:
+                continue
+            want[b, ty0:ty1 + 1, tx0:tx1 + 1] += 1
+    assert (counts.reshape(B, S // 16, S // 16) == want).all()
+    assert counts.max() > 0
+    # the image does not depend on the schedule: the same items rendered two at a time (512 CTAs < 2 waves: no list).  Two, because
+    # the last face of an item reads its successor's texel (quirk Q3), so item b needs item b + 1 behind it to see the same bytes.
+    two, agg2 = torch.empty(2, 4, S, S, device=dev), torch.empty(2, 2, S, S, device=dev)
+    ws2 = torch.empty(lib.gendr_workspace_bytes(2, F), dtype=torch.uint8, device=dev)
+    for b in (0, 7, B - 2):
+        _lib.check(lib.gendr_forward_render(faces[b:b + 2].data_ptr(), tex[b:b + 2].data_ptr(), None, agg2.data_ptr(), two.data_ptr(), 2, F, 1,
+                                            C.byref(params), 0, ws2.data_ptr(), ws2.numel(), None))
+        assert torch.equal(two[0], colors[b]), b
+        if b == B - 2:
+            assert torch.equal(two[1], colors[B - 1])
