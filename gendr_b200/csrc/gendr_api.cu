@@ -258,12 +258,12 @@ static uint2* ws_rects(void* ws, int B, int F) {
 }
 
 // longest-first schedule: [counts B*tiles | order B*tiles] (uint32) behind the rectangles; 32 KB per batch item hold up to 4096
-// tiles per image (image_size <= 1024).  Used when the grid is at least two waves of the machine -- below that every CTA is
-// resident from the start and the order is irrelevant.
+// tiles per image (image_size <= 1024).  Used when the grid is more than one wave of the machine (148 SMs x 4 CTAs) -- up to
+// that every CTA is resident from the start and the order is irrelevant.
 static const size_t kLptBytesPerItem = 32768;
 static bool lpt_enabled(const RenderParams& P) {
     const long long tiles = (long long)P.tiles_x * P.tiles_y, n = tiles * P.B;
-    return n >= 2 * 148 * 4 && tiles * 8 <= (long long)kLptBytesPerItem && n <= (1ll << 18);
+    return n > 148 * 4 && tiles * 8 <= (long long)kLptBytesPerItem && n <= (1ll << 18);
 }
 static unsigned* ws_tile_counts(void* ws, int B, int F) {
     size_t rct_bytes = ((size_t)B * F * sizeof(uint2) + 255) & ~(size_t)255;
@@ -339,7 +339,7 @@ static int run_render(const RenderParams& P, const KernelIO& io, bool backward, 
                 (P.aggr_alpha_func == T_PROBABILISTIC || P.aggr_alpha_func == T_EINSTEIN || yager2));
     cfg.tcn_mode = cfg.fast ? (yager2 ? 4 : P.aggr_alpha_func) : (P.aggr_alpha_func >= T_HAMACHER ? 1 : 0);
     KernelIO io2 = io;      // (records = start of the workspace)
-    io2.cta_order = (lpt_enabled(P) && cfg.grid.y == 1) ? ws_cta_order(const_cast<float*>(io.records), P) : nullptr;
+    io2.cta_order = lpt_enabled(P) ? ws_cta_order(const_cast<float*>(io.records), P) : nullptr;      // (indexed by blockIdx.x, whatever gridDim.y)
     cudaError_t e = kLaunchTable[P.dist_func](P, io2, cfg);
     g_launches++;
     if (e != cudaSuccess) return fail((int)e, backward ? "backward render_kernel launch" : "forward render_kernel launch");
