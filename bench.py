@@ -77,11 +77,16 @@ def csrc_sha():
     """Fingerprint of the kernel sources: ncu-derived constants in profiles/roofline_traffic.json are only used when they were
     captured from exactly these sources."""
     import hashlib
+    import re
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'gendr_b200', 'csrc')
     for name in sorted(os.listdir(d)):
         if name.endswith(('.cu', '.cuh')):
-            h.update(open(os.path.join(d, name), 'rb').read())
+            text = open(os.path.join(d, name), 'r', encoding='utf-8', errors='replace').read()
+            # the CODE: comments and whitespace do not change the kernels (the sources hold no string literal with // or /* in it)
+            text = re.sub(r'/\*.*?\*/', ' ', text, flags=re.S)
+            text = re.sub(r'//[^\n]*', ' ', text)
+            h.update(' '.join(text.split()).encode())
     return h.hexdigest()[:16]
 
 

@@ -161,7 +161,7 @@ def test_batch_summed_backward_equals_sum_of_per_item_gradients():
 
 
 def test_sorted_cta_schedule_is_a_permutation_heaviest_first():
-    """Grids of >= 2 waves of CTAs run longest-first within groups of 16 batch items (tile_order_kernel): the list the render kernels
+    """Grids of more than one wave of CTAs (148 SMs x 4) run longest-first within groups of 16 batch items (tile_order_kernel): the list the render kernels
     index with blockIdx.x must contain every (item, tile) exactly once, grouped by item group, with the candidate counts (exact below
     128 faces, binned by 16 above) non-increasing inside a group; the counts must equal a host recount from the packed rectangles."""
     dev = _dev()
@@ -203,7 +203,7 @@ def test_sorted_cta_schedule_is_a_permutation_heaviest_first():
             want[b, ty0:ty1 + 1, tx0:tx1 + 1] += 1
     assert (counts.reshape(B, S // 16, S // 16) == want).all()
     assert counts.max() > 0
-    # the image does not depend on the schedule: the same items rendered two at a time (512 CTAs < 2 waves: no list).  Two, because
+    # the image does not depend on the schedule: the same items rendered two at a time (512 CTAs: at most one wave, no list).  Two, because
     # the last face of an item reads its successor's texel (quirk Q3), so item b needs item b + 1 behind it to see the same bytes.
     two, agg2 = torch.empty(2, 4, S, S, device=dev), torch.empty(2, 2, S, S, device=dev)
     ws2 = torch.empty(lib.gendr_workspace_bytes(2, F), dtype=torch.uint8, device=dev)

@@ -268,7 +268,7 @@ def test_edge_cases(gpu_oracle):
     out = gd.functional.render(torch.zeros(2, 0, 3, 3, device=dev), torch.zeros(2, 0, 1, 3, device=dev), image_size=16, background_color=[0.5, 0.25, 0.125])
     assert out.shape == (2, 4, 16, 16) and float(out[:, 3].abs().max()) == 0.0
     assert torch.allclose(out[:, 0], torch.full((2, 16, 16), 0.5, device=dev)) and torch.allclose(out[:, 2], torch.full((2, 16, 16), 0.125, device=dev))
-    # ... and on a grid large enough for the sorted CTA schedule (>= 2 waves of CTAs): every tile must still be rendered once
+    # ... and on a grid large enough for the sorted CTA schedule (more than one wave of CTAs): every tile must still be rendered once
     for fn, args in ((gd.functional.render, (torch.zeros(8, 0, 3, 3, device=dev), torch.zeros(8, 0, 1, 3, device=dev))),
                      (gd.functional.render_indexed, (torch.zeros(8, 5, 3, device=dev), torch.zeros(8, 0, 3, dtype=torch.int32, device=dev),
                                                      torch.zeros(8, 0, 1, 3, device=dev)))):

@@ -29,7 +29,7 @@ img = gd.functional.render_scene(v, faces.to(dev), tex, eyes, camera=dict(viewin
                                  dist_scale=0.03, anti_aliasing=True)
 img.backward(torch.ones_like(img)); torch.cuda.synchronize()
 print('scene', float(img.sum()), float(v.grad.abs().sum()), float(eyes.grad.abs().sum()))
-# a grid of >= 2 waves of CTAs (5 x 256 tiles): tile counters, the counting sort and the sorted CTA schedule; vertex-texture lighting
+# a grid of more than one wave of CTAs (5 x 256 tiles): tile counters, the counting sort and the sorted CTA schedule; vertex-texture lighting
 fv, ft = scenes.soup(60, batch=5, seed=7, size=0.3)
 a, b = fv.to(dev).requires_grad_(True), ft.to(dev).requires_grad_(True)
 img = gd.functional.render(a, b, image_size=256, dist_func='gaussian', aggr_alpha_func='einstein', dist_scale=0.01, dist_eps=30.)
