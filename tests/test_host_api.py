@@ -207,3 +207,23 @@ def test_cpp_autograd_node_is_built_and_consistent():
     p.image_size = 8
     with pytest.raises(TypeError):
         _torchbind.render_faces(torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 1, 3), C.addressof(p), False)
+
+
+def test_source_fingerprint_ignores_comments_only(tmp_path, monkeypatch):
+    """bench.csrc_sha keys the ncu-derived roofline constants on the kernel CODE: comments and whitespace must not change it,
+    any token must; and the committed constants must belong to the sources in the tree."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    committed = json.load(open(os.path.join(bench.ROOT, 'profiles', 'roofline_traffic.json')))
+    assert committed['csrc_sha'] == bench.csrc_sha(), 'profiles/roofline_traffic.json was captured from other kernel sources'
+    d = tmp_path / 'gendr_b200' / 'csrc'
+    d.mkdir(parents=True)
+    monkeypatch.setattr(bench, 'ROOT', str(tmp_path))
+    (d / 'k.cuh').write_text('__global__ void k(float* p) {\n    p[0] = 1.f;   // one\n}\n')
+    a = bench.csrc_sha()
+    (d / 'k.cuh').write_text('/* header\n   comment */\n__global__ void k(float* p)\n{\n  p[0] = 1.f;      // a different comment\n}\n')
+    assert bench.csrc_sha() == a
+    (d / 'k.cuh').write_text('__global__ void k(float* p) {\n    p[0] = 2.f;   // one\n}\n')
+    assert bench.csrc_sha() != a
